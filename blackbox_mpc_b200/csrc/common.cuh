@@ -1,0 +1,116 @@
+// common.cuh — context / model structures shared by the translation units of libbbmpc.so.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/bbmpc.h"
+
+namespace bbmpc {
+
+constexpr int MAX_LAYERS = 8;
+constexpr int MAX_MEMBERS = 16;
+constexpr int MAX_DS = 64;
+constexpr int MAX_DU = 32;
+constexpr int BIAS_COLS = 3;  // bias enters the tensor-core GEMM as 3 bf16 rows times ones-columns
+
+// Normalisation statistics as the kernels consume them (all device pointers into one buffer).
+// den_* = std + 1e-7 rounded once in fp32, exactly the reference's (std + 1e-7) sub-expression
+// (dynamics_handlers/system_dynamics_handler.py:119-124,153-156).
+struct NormDev {
+  int enabled;
+  const float *mean_s, *den_s, *mean_a, *den_a, *mean_t, *den_t;
+};
+
+// One layer of the fp32 image used by the SIMT kernels: W32[K][ldw] (ldw = N rounded up to 16,
+// zero padded), b32[ldw].  Offsets are in floats from MlpDev::w32, per member.
+struct LayerDev {
+  int K, N, ldw, act;
+  int64_t w_off, b_off;  // member 0; member m adds m * MlpDev::w_member_stride
+  // tensor-core image: Kpad/16 chunks per (member, layer); chunk c of member m starts at
+  // img_off + m*img_member_stride + c*chunk_bytes and holds [hi: 2 x Npad x 16B][lo: 2 x Npad x 16B].
+  int Kpad, Npad, chunk_bytes;
+  int64_t img_off;
+};
+
+struct MlpDev {
+  int n_members, n_layers;
+  int64_t w_member_stride, img_member_stride;  // floats / bytes
+  LayerDev layer[MAX_LAYERS];
+  const float* w32;
+  const uint8_t* wimg;   // nullptr when the model does not fit the tensor-core path
+  const uint2* chunk_table;  // per step: (byte offset into wimg, bytes) for every chunk in issue order
+  int chunks_per_step;
+  int max_width;   // widest activation (incl. input) — SIMT smem sizing
+};
+
+struct ModelHost {
+  bool set = false;
+  int dyn_id = BBMPC_DYN_MLP;
+  int dS = 0, dU = 0;
+  MlpDev mlp{};
+  NormDev norm{};
+  float* w32_buf = nullptr;
+  uint8_t* wimg_buf = nullptr;
+  uint2* chunk_table_buf = nullptr;
+  float* norm_buf = nullptr;
+  bool tc_ok = false;
+  std::string tc_why;  // why the tensor-core path is unavailable for this model
+};
+
+}  // namespace bbmpc
+
+struct bbmpc_ctx {
+  int device = 0;
+  uint64_t seed = 0;
+  int sm_count = 148;
+  int prec = BBMPC_PREC_AUTO;
+  int reward_id = 0;
+  bbmpc::ModelHost model;
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace bbmpc {
+
+int fail(bbmpc_ctx* ctx, int code, const char* fmt, ...);
+
+#define BB_CUDA(ctx, expr)                                                                   \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return ::bbmpc::fail((ctx), BBMPC_ECUDA, "%s failed: %s (%s:%d)", #expr,               \
+                           cudaGetErrorString(e_), __FILE__, __LINE__);                      \
+  } while (0)
+
+#define BB_LAUNCH_CHECK(ctx)                                                                 \
+  do {                                                                                       \
+    cudaError_t e_ = cudaGetLastError();                                                     \
+    if (e_ != cudaSuccess)                                                                   \
+      return ::bbmpc::fail((ctx), BBMPC_ECUDA, "kernel launch failed: %s (%s:%d)",           \
+                           cudaGetErrorString(e_), __FILE__, __LINE__);                      \
+    (ctx)->launches++;                                                                       \
+  } while (0)
+
+// ---- kernel launchers implemented per translation unit
+struct StepIO {  // one predict/reward step over B rows (optimizer tail, predict_next_state, ...)
+  const float* s; const float* a; const float* s2_in; float* s2_out; float* reward_out; float* raw_out;
+  int B; int mode;  // mode bits: 1 = predict next state, 2 = reward, 4 = raw dynamics_function on x=s
+};
+int launch_rollout_simt(bbmpc_ctx* ctx, const float* states, const float* actions, float* returns,
+                        const float* penalty, int rows, int A, int H, int act_ld, cudaStream_t st);
+int launch_step_simt(bbmpc_ctx* ctx, const StepIO& io, cudaStream_t st);
+int launch_rollout_tc(bbmpc_ctx* ctx, const float* states, const float* actions, float* returns,
+                      const float* penalty, int rows, int A, int H, int passes, cudaStream_t st);
+int pack_tc_image(bbmpc_ctx* ctx, cudaStream_t st);   // builds model.wimg from model.w32
+bool tc_supported(const ModelHost& m, std::string* why);
+int tc_du_slots(int dU);  // action slots at the head of the layer-0 K axis (8 or 16)
+int resolve_precision(const bbmpc_ctx* ctx);
+// rollout dispatch used by bbmpc_rollout and the optimizers.  `penalty` (nullable, [rows]) is
+// subtracted from the return before the NaN guard is applied?  No: the reference applies the NaN
+// guard inside the evaluator and subtracts the penalty outside, so penalty is subtracted AFTER.
+int rollout_dispatch(bbmpc_ctx* ctx, const float* states, const float* actions, float* returns,
+                     const float* penalty, int rows, int A, int H, cudaStream_t st);
+
+}  // namespace bbmpc

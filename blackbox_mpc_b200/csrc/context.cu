@@ -1,0 +1,372 @@
+// context.cu — context lifetime, model staging (fp32 image + bf16 hi/lo tensor-core image),
+// evaluator-level C-ABI entry points.
+#include <cstdarg>
+#include <cstring>
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "device_fns.cuh"
+
+namespace bbmpc {
+
+static std::string g_create_err;
+
+int fail(bbmpc_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_err = buf;
+  return code;
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------- staging kernels
+__global__ void copy_pad_kernel(const float* __restrict__ src, float* __restrict__ dst, int K, int N,
+                                int ldw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * ldw) return;
+  const int k = i / ldw, n = i % ldw;
+  dst[i] = n < N ? src[static_cast<size_t>(k) * N + n] : 0.0f;
+}
+
+// Tensor-core image of one (member, layer): weight rows split hi + lo; three rows hold the bias as
+// bf16 terms (b = b1 + b2 + b3 to 24 bits) that meet ones-columns of the A operand; the rest is
+// zero.  Image row order: hidden layers [w_0..w_{K-1} | bias x3]; layer 0 (du_slots > 0) is
+// [action rows padded to du_slots | state rows | bias x3] so that the epilogue can assemble its
+// input with compile-time register indices.
+__global__ void pack_tc_kernel(const float* __restrict__ W, const float* __restrict__ b,
+                               uint8_t* __restrict__ img, int K, int N, int ldw, int Kpad, int Npad,
+                               int du_slots, int dS, int dU) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Kpad * Npad) return;
+  const int k = i / Npad, n = i % Npad;
+  int src = -1, bias_term = -1;
+  if (du_slots > 0) {
+    if (k < du_slots) src = (k < dU) ? dS + k : -1;
+    else if (k - du_slots < dS) src = k - du_slots;
+    else if (k - du_slots - dS < BIAS_COLS) bias_term = k - du_slots - dS;
+  } else {
+    if (k < K) src = k;
+    else if (k - K < BIAS_COLS) bias_term = k - K;
+  }
+  __nv_bfloat16 hi = __float2bfloat16(0.0f), lo = hi;
+  if (n < N) {
+    if (src >= 0) {
+      const float v = W[static_cast<size_t>(src) * ldw + n];
+      hi = __float2bfloat16_rn(v);
+      lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    } else if (bias_term >= 0) {
+      float r = b[n];
+      __nv_bfloat16 t = __float2bfloat16_rn(r);
+      for (int j = 0; j < bias_term; ++j) { r -= __bfloat162float(t); t = __float2bfloat16_rn(r); }
+      hi = t;
+    }
+  }
+  const int chunk = k >> 4, kk = k & 15;
+  const size_t chunk_bytes = static_cast<size_t>(Npad) * 64;
+  const size_t off = chunk * chunk_bytes + (static_cast<size_t>(kk >> 3) * Npad + n) * 16 + (kk & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(img + off) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(img + off + static_cast<size_t>(Npad) * 32) = lo;
+}
+
+__global__ void norm_prepare_kernel(const float* __restrict__ std_in, float* __restrict__ den, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) den[i] = __fadd_rn(std_in[i], 1e-7f);
+}
+
+// ---------------------------------------------------------------------------- tensor-core eligibility
+bool tc_supported(const ModelHost& m, std::string* why) {
+  auto no = [&](const char* s) { if (why) *why = s; return false; };
+  if (m.dyn_id != BBMPC_DYN_MLP) return no("analytical dynamics has no GEMM");
+  const MlpDev& p = m.mlp;
+  if (m.dS > 32 || m.dU > 16) return no("dS > 32 or dU > 16");
+  int d_main = 0, a_cols = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const LayerDev& L = p.layer[l];
+    if (L.Npad > 256 || L.Kpad > 256) return no("layer wider than 253");
+    if (l < p.n_layers - 1 && L.Npad > d_main) d_main = L.Npad;
+    if (l > 0 && L.Kpad > a_cols) a_cols = L.Kpad;
+  }
+  const int total = d_main + p.layer[p.n_layers - 1].Npad + p.layer[0].Kpad + a_cols;
+  if (total > 512) return no("TMEM budget exceeded (D + Dout + X + A > 512 columns)");
+  if (p.layer[p.n_layers - 1].N != m.dS) return no("output width != dS");
+  if (p.n_members > 1 && p.layer[p.n_layers - 1].act != BBMPC_ACT_NONE)
+    return no("ensemble with a non-linear output layer");
+  return true;
+}
+
+int resolve_precision(const bbmpc_ctx* ctx) {
+  if (ctx->model.dyn_id != BBMPC_DYN_MLP) return BBMPC_PREC_FP32;
+  if (ctx->prec == BBMPC_PREC_AUTO) return ctx->model.tc_ok ? BBMPC_PREC_BF16X3 : BBMPC_PREC_FP32;
+  return ctx->prec;
+}
+
+static void free_model(ModelHost& m) {
+  cudaFree(m.w32_buf); cudaFree(m.wimg_buf); cudaFree(m.chunk_table_buf);
+  m.w32_buf = nullptr; m.wimg_buf = nullptr; m.chunk_table_buf = nullptr;
+  m.mlp = MlpDev{};
+  m.tc_ok = false;
+  m.set = false;
+}
+
+int rollout_dispatch(bbmpc_ctx* ctx, const float* states, const float* actions, float* returns,
+                     const float* penalty, int rows, int A, int H, cudaStream_t st) {
+  if (!ctx->model.set) return fail(ctx, BBMPC_ESTATE, "rollout before a dynamics model was set");
+  if (!ctx->reward_id) return fail(ctx, BBMPC_ESTATE, "rollout before a reward function was set");
+  const int prec = resolve_precision(ctx);
+  if (prec == BBMPC_PREC_FP32)
+    return launch_rollout_simt(ctx, states, actions, returns, penalty, rows, A, H, 0, st);
+  if (!ctx->model.tc_ok)
+    return fail(ctx, BBMPC_EINVAL, "tensor-core precision requested but the model does not fit it: %s",
+                ctx->model.tc_why.c_str());
+  return launch_rollout_tc(ctx, states, actions, returns, penalty, rows, A, H,
+                           prec == BBMPC_PREC_BF16 ? 1 : 3, st);
+}
+
+}  // namespace bbmpc
+
+using namespace bbmpc;
+
+extern "C" {
+
+int bbmpc_version(void) { return 100; }
+
+const char* bbmpc_last_error(const bbmpc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int bbmpc_ctx_create(int device, uint64_t seed, bbmpc_ctx** out) {
+  if (!out) return fail(nullptr, BBMPC_EINVAL, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, BBMPC_ECUDA, "no CUDA device available (%s); libbbmpc has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= n) return fail(nullptr, BBMPC_EINVAL, "device %d out of range [0,%d)", device, n);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return fail(nullptr, BBMPC_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, BBMPC_ECUDA, "device %d is sm_%d%d; libbbmpc is built for sm_100a only", device,
+                prop.major, prop.minor);
+  if ((e = cudaSetDevice(device)) != cudaSuccess)
+    return fail(nullptr, BBMPC_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  bbmpc_ctx* c = new bbmpc_ctx();
+  c->device = device;
+  c->seed = seed;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return BBMPC_OK;
+}
+
+void bbmpc_ctx_destroy(bbmpc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  free_model(ctx->model);
+  cudaFree(ctx->model.norm_buf);
+  delete ctx;
+}
+
+int bbmpc_set_precision(bbmpc_ctx* ctx, int prec) {
+  if (!ctx) return BBMPC_EINVAL;
+  if (prec < BBMPC_PREC_AUTO || prec > BBMPC_PREC_BF16) return fail(ctx, BBMPC_EINVAL, "unknown precision %d", prec);
+  ctx->prec = prec;
+  return BBMPC_OK;
+}
+
+int bbmpc_get_effective_precision(const bbmpc_ctx* ctx) { return ctx ? resolve_precision(ctx) : BBMPC_EINVAL; }
+
+uint64_t bbmpc_launch_count(const bbmpc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int bbmpc_model_set_mlp(bbmpc_ctx* ctx, int n_members, int n_layers, const int* dims,
+                        const float* const* W, const float* const* b, const int* act_ids, void* stream) {
+  if (!ctx) return BBMPC_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_members < 1 || n_members > MAX_MEMBERS) return fail(ctx, BBMPC_EINVAL, "n_members %d not in [1,%d]", n_members, MAX_MEMBERS);
+  if (n_layers < 1 || n_layers > MAX_LAYERS) return fail(ctx, BBMPC_EINVAL, "n_layers %d not in [1,%d]", n_layers, MAX_LAYERS);
+  if (!dims || !W || !b || !act_ids) return fail(ctx, BBMPC_EINVAL, "NULL argument");
+  for (int l = 0; l <= n_layers; ++l)
+    if (dims[l] < 1 || dims[l] > 4096) return fail(ctx, BBMPC_EINVAL, "layer width %d unsupported", dims[l]);
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ModelHost& m = ctx->model;
+  BB_CUDA(ctx, cudaStreamSynchronize(st));  // nothing in flight may still read the old image
+  free_model(m);
+  m.dyn_id = BBMPC_DYN_MLP;
+  MlpDev& p = m.mlp;
+  p.n_members = n_members;
+  p.n_layers = n_layers;
+  // dS/dU are fixed by set_norm / opt_create when called first; else infer them from the dims
+  if (m.dS == 0) { m.dS = dims[n_layers]; m.dU = dims[0] - dims[n_layers]; }
+  if (m.dS + m.dU != dims[0] || m.dS != dims[n_layers])
+    return fail(ctx, BBMPC_EINVAL, "MLP dims [%d -> %d] do not match dS=%d dU=%d", dims[0], dims[n_layers], m.dS, m.dU);
+  if (m.dS > MAX_DS || m.dU > MAX_DU || m.dU < 1) return fail(ctx, BBMPC_EINVAL, "dS=%d dU=%d unsupported (max %d/%d)", m.dS, m.dU, MAX_DS, MAX_DU);
+  int64_t w_floats = 0, img_bytes = 0;
+  p.max_width = dims[0];
+  for (int l = 0; l < n_layers; ++l) {
+    LayerDev& L = p.layer[l];
+    L.K = dims[l]; L.N = dims[l + 1]; L.ldw = round_up(L.N, 16); L.act = act_ids[l];
+    if (L.act < BBMPC_ACT_NONE || L.act > BBMPC_ACT_SIGMOID) return fail(ctx, BBMPC_EINVAL, "unknown activation id %d", L.act);
+    L.Kpad = round_up((l == 0 ? L.K - m.dU + tc_du_slots(m.dU) : L.K) + BIAS_COLS, 16);
+    L.Npad = round_up(L.N, 16);
+    L.chunk_bytes = L.Npad * 64;
+    if (L.N > p.max_width) p.max_width = L.N;
+    L.w_off = w_floats; w_floats += static_cast<int64_t>(L.K) * L.ldw;
+    L.b_off = w_floats; w_floats += L.ldw;
+    L.img_off = img_bytes; img_bytes += static_cast<int64_t>(L.Kpad / 16) * L.chunk_bytes;
+  }
+  p.w_member_stride = w_floats;
+  p.img_member_stride = img_bytes;
+  w_floats *= n_members;
+  img_bytes *= n_members;
+  BB_CUDA(ctx, cudaMalloc(&m.w32_buf, w_floats * sizeof(float)));
+  BB_CUDA(ctx, cudaMemsetAsync(m.w32_buf, 0, w_floats * sizeof(float), st));
+  for (int l = 0; l < n_layers; ++l) {
+    const LayerDev& L = p.layer[l];
+    for (int mm = 0; mm < n_members; ++mm) {
+      const float* Wsrc = W[mm * n_layers + l];
+      const float* bsrc = b[mm * n_layers + l];
+      if (!Wsrc || !bsrc) return fail(ctx, BBMPC_EINVAL, "NULL weight pointer (member %d layer %d)", mm, l);
+      const int n = L.K * L.ldw;
+      copy_pad_kernel<<<(n + 255) / 256, 256, 0, st>>>(Wsrc, m.w32_buf + L.w_off + mm * p.w_member_stride, L.K, L.N, L.ldw);
+      BB_LAUNCH_CHECK(ctx);
+      BB_CUDA(ctx, cudaMemcpyAsync(m.w32_buf + L.b_off + mm * p.w_member_stride, bsrc, L.N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  p.w32 = m.w32_buf;
+  m.set = true;
+  // tensor-core image
+  m.tc_ok = tc_supported(m, &m.tc_why);
+  if (m.tc_ok) {
+    BB_CUDA(ctx, cudaMalloc(&m.wimg_buf, img_bytes));
+    std::vector<uint2> table;
+    for (int mm = 0; mm < n_members; ++mm)
+      for (int l = 0; l < n_layers; ++l) {
+        const LayerDev& L = p.layer[l];
+        const int n = L.Kpad * L.Npad;
+        const int64_t io = L.img_off + mm * p.img_member_stride;
+        pack_tc_kernel<<<(n + 255) / 256, 256, 0, st>>>(m.w32_buf + L.w_off + mm * p.w_member_stride,
+                                                       m.w32_buf + L.b_off + mm * p.w_member_stride,
+                                                       m.wimg_buf + io, L.K, L.N, L.ldw, L.Kpad, L.Npad,
+                                                       l == 0 ? tc_du_slots(m.dU) : 0, m.dS, m.dU);
+        BB_LAUNCH_CHECK(ctx);
+        for (int c = 0; c < L.Kpad / 16; ++c)
+          table.push_back(make_uint2(static_cast<uint32_t>(io + static_cast<int64_t>(c) * L.chunk_bytes),
+                                     static_cast<uint32_t>(L.chunk_bytes)));
+      }
+    BB_CUDA(ctx, cudaMalloc(&m.chunk_table_buf, table.size() * sizeof(uint2)));
+    BB_CUDA(ctx, cudaMemcpyAsync(m.chunk_table_buf, table.data(), table.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+    BB_CUDA(ctx, cudaStreamSynchronize(st));  // `table` is a stack-lifetime host buffer
+    p.wimg = m.wimg_buf;
+    p.chunk_table = m.chunk_table_buf;
+    p.chunks_per_step = static_cast<int>(table.size());
+  }
+  return BBMPC_OK;
+}
+
+int bbmpc_model_set_norm(bbmpc_ctx* ctx, int dS, int dU, const float* mean_s, const float* std_s,
+                         const float* mean_a, const float* std_a, const float* mean_t, const float* std_t,
+                         void* stream) {
+  if (!ctx) return BBMPC_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dS < 1 || dS > MAX_DS || dU < 1 || dU > MAX_DU) return fail(ctx, BBMPC_EINVAL, "dS=%d dU=%d unsupported", dS, dU);
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ModelHost& m = ctx->model;
+  if (m.set && m.dyn_id == BBMPC_DYN_MLP && (m.dS != dS || m.dU != dU))
+    return fail(ctx, BBMPC_EINVAL, "norm dims dS=%d dU=%d differ from the model's dS=%d dU=%d", dS, dU, m.dS, m.dU);
+  m.dS = dS; m.dU = dU;
+  const int n_null = !mean_s + !std_s + !mean_a + !std_a + !mean_t + !std_t;
+  if (n_null == 6) { m.norm = NormDev{}; return BBMPC_OK; }
+  if (n_null != 0) return fail(ctx, BBMPC_EINVAL, "normalisation statistics must be all set or all NULL");
+  if (!m.norm_buf) BB_CUDA(ctx, cudaMalloc(&m.norm_buf, (4 * MAX_DS + 2 * MAX_DU) * sizeof(float)));
+  float* base = m.norm_buf;
+  float *ms = base, *ds = base + MAX_DS, *mt = base + 2 * MAX_DS, *dt = base + 3 * MAX_DS,
+        *ma = base + 4 * MAX_DS, *da = base + 4 * MAX_DS + MAX_DU;
+  BB_CUDA(ctx, cudaMemcpyAsync(ms, mean_s, dS * 4, cudaMemcpyDeviceToDevice, st));
+  BB_CUDA(ctx, cudaMemcpyAsync(mt, mean_t, dS * 4, cudaMemcpyDeviceToDevice, st));
+  BB_CUDA(ctx, cudaMemcpyAsync(ma, mean_a, dU * 4, cudaMemcpyDeviceToDevice, st));
+  norm_prepare_kernel<<<1, 64, 0, st>>>(std_s, ds, dS); BB_LAUNCH_CHECK(ctx);
+  norm_prepare_kernel<<<1, 64, 0, st>>>(std_t, dt, dS); BB_LAUNCH_CHECK(ctx);
+  norm_prepare_kernel<<<1, 64, 0, st>>>(std_a, da, dU); BB_LAUNCH_CHECK(ctx);
+  m.norm = NormDev{1, ms, ds, ma, da, mt, dt};
+  return BBMPC_OK;
+}
+
+int bbmpc_model_set_builtin(bbmpc_ctx* ctx, int dyn_id, int dS, int dU) {
+  if (!ctx) return BBMPC_EINVAL;
+  if (dyn_id != BBMPC_DYN_PENDULUM) return fail(ctx, BBMPC_EINVAL, "unknown builtin dynamics id %d", dyn_id);
+  if (dS != 3 || dU != 1) return fail(ctx, BBMPC_EINVAL, "pendulum model needs dS=3 dU=1 (got %d, %d)", dS, dU);
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  BB_CUDA(ctx, cudaDeviceSynchronize());
+  free_model(ctx->model);
+  ctx->model.dyn_id = dyn_id;
+  ctx->model.dS = dS; ctx->model.dU = dU;
+  ctx->model.norm = NormDev{};
+  ctx->model.set = true;
+  ctx->model.tc_why = "analytical dynamics has no GEMM";
+  return BBMPC_OK;
+}
+
+int bbmpc_reward_set_builtin(bbmpc_ctx* ctx, int reward_id) {
+  if (!ctx) return BBMPC_EINVAL;
+  if (reward_id < BBMPC_REWARD_PENDULUM || reward_id > BBMPC_REWARD_PENDULUM_GYM)
+    return fail(ctx, BBMPC_EINVAL, "unknown reward id %d", reward_id);
+  ctx->reward_id = reward_id;
+  return BBMPC_OK;
+}
+
+static int check_reward_dims(bbmpc_ctx* ctx) {
+  const ModelHost& m = ctx->model;
+  if (ctx->reward_id == BBMPC_REWARD_HALFCHEETAH && m.dS < 18)
+    return fail(ctx, BBMPC_EINVAL, "HalfCheetah reward reads state[17]; dS=%d", m.dS);
+  if ((ctx->reward_id == BBMPC_REWARD_PENDULUM || ctx->reward_id == BBMPC_REWARD_PENDULUM_GYM) && m.dS < 3)
+    return fail(ctx, BBMPC_EINVAL, "pendulum reward reads state[0..2]; dS=%d", m.dS);
+  return BBMPC_OK;
+}
+
+int bbmpc_rollout(bbmpc_ctx* ctx, const float* states, const float* actions, float* returns, int P, int A,
+                  int H, void* stream) {
+  if (!ctx) return BBMPC_EINVAL;
+  if (P < 0 || A < 1 || H < 0) return fail(ctx, BBMPC_EINVAL, "bad shape P=%d A=%d H=%d", P, A, H);
+  if (P == 0) return BBMPC_OK;
+  if (!states || !actions || !returns) return fail(ctx, BBMPC_EINVAL, "NULL pointer");
+  if (int rc = check_reward_dims(ctx)) return rc;
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return rollout_dispatch(ctx, states, actions, returns, nullptr, P * A, A, H, static_cast<cudaStream_t>(stream));
+}
+
+int bbmpc_predict_next_state(bbmpc_ctx* ctx, const float* s, const float* a, float* out, int B, void* stream) {
+  if (!ctx) return BBMPC_EINVAL;
+  if (!ctx->model.set) return fail(ctx, BBMPC_ESTATE, "predict_next_state before a dynamics model was set");
+  if (B <= 0) return B == 0 ? BBMPC_OK : fail(ctx, BBMPC_EINVAL, "B < 0");
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  StepIO io{s, a, nullptr, out, nullptr, nullptr, B, 1};
+  return launch_step_simt(ctx, io, static_cast<cudaStream_t>(stream));
+}
+
+int bbmpc_reward(bbmpc_ctx* ctx, const float* s, const float* a, const float* s2, float* out, int B, void* stream) {
+  if (!ctx) return BBMPC_EINVAL;
+  if (!ctx->reward_id) return fail(ctx, BBMPC_ESTATE, "reward before a reward function was set");
+  if (!ctx->model.dS) return fail(ctx, BBMPC_ESTATE, "reward before dS/dU are known (set a model first)");
+  if (int rc = check_reward_dims(ctx)) return rc;
+  if (B <= 0) return B == 0 ? BBMPC_OK : fail(ctx, BBMPC_EINVAL, "B < 0");
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  StepIO io{s, a, s2, nullptr, out, nullptr, B, 2};
+  return launch_step_simt(ctx, io, static_cast<cudaStream_t>(stream));
+}
+
+int bbmpc_dynamics_forward(bbmpc_ctx* ctx, const float* x, float* out, int B, void* stream) {
+  if (!ctx) return BBMPC_EINVAL;
+  if (!ctx->model.set) return fail(ctx, BBMPC_ESTATE, "dynamics_forward before a dynamics model was set");
+  if (B <= 0) return B == 0 ? BBMPC_OK : fail(ctx, BBMPC_EINVAL, "B < 0");
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  StepIO io{x, nullptr, nullptr, nullptr, nullptr, out, B, 4};
+  return launch_step_simt(ctx, io, static_cast<cudaStream_t>(stream));
+}
+
+void bbmpc_philox4x32_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  const Philox4 r = philox4x32_10(Philox4{ctr[0], ctr[1], ctr[2], ctr[3]}, key[0], key[1]);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+}  // extern "C"

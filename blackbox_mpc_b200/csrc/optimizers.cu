@@ -1,0 +1,899 @@
+// optimizers.cu — sampling + refit kernels and host orchestration of the six reference
+// optimizers (optimizers/{cem,pi2,random_search,pso,spsa,cma_es}.py) behind bbmpc_opt_*.
+//
+// Every optimizer iteration is "local" (sample this rank's slice of the population, roll it out,
+// reduce it to a small partial message) followed by "merge" (combine the partial messages of all
+// ranks, identical arithmetic on every rank, update the search distribution).  With one GPU the
+// two halves run back to back; with several, the host all-gathers the partials in between.
+// Draws are Philox streams keyed on (seed, act-call, stream, iteration, GLOBAL row): results do
+// not depend on how the population is sharded.
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include "common.cuh"
+#include "device_fns.cuh"
+#include "refit.cuh"
+
+using namespace bbmpc;
+
+// ============================================================================ handle
+struct bbmpc_opt {
+  bbmpc_ctx* ctx = nullptr;
+  bbmpc_opt_config cfg{};
+  int rank = 0, world = 1;
+  int p0 = 0, P_local = 0;        // this rank's slice [p0, p0 + P_local) of the population
+  int n_eval = 0;                 // rows of the population axis handed to the evaluator (SPSA: 2*P_local)
+  int HU = 0, AHU = 0;            // H*dU, A*H*dU
+  uint32_t act_call = 0;
+  int time_step = 0;
+  bool began = false;
+  // device state
+  float *d_lb = nullptr, *d_ub = nullptr;
+  float* d_state = nullptr;       // [A,dS]
+  float* d_samples = nullptr;     // [n_eval, A, H, dU]
+  float* d_returns = nullptr;     // [n_eval, A]
+  float* d_penalty = nullptr;     // [n_eval, A]
+  float* d_mean = nullptr;        // loop variable  [A,H,dU]
+  float* d_var = nullptr;         // loop variable  [A,H,dU] (CEM)
+  float* d_prev = nullptr;        // persistent "previous solution" / current parameters [A,H,dU]
+  float* d_var0 = nullptr;        // persistent solution variance [A,H,dU]
+  float* d_partial = nullptr;     // [partial_floats]
+  float* d_action = nullptr;      // [A,dU]
+  float* d_next = nullptr;        // [A,dS]
+  float* d_reward = nullptr;      // [A]
+  // PSO
+  float *d_v = nullptr, *d_pbx = nullptr, *d_pbr = nullptr, *d_gbx = nullptr, *d_gbr = nullptr, *d_sol = nullptr;
+  // CMA-ES
+  float *d_m = nullptr, *d_sigma = nullptr, *d_C = nullptr, *d_B = nullptr, *d_D = nullptr, *d_ps = nullptr,
+        *d_pc = nullptr, *d_z = nullptr, *d_BD = nullptr, *d_work = nullptr, *d_cma_w = nullptr;
+  double cma_consts[16] = {0};
+  // trace + pinned staging
+  float* trace = nullptr; int64_t trace_floats = 0;
+  float* h_pinned = nullptr;
+  std::vector<void*> owned;
+};
+
+namespace {
+
+int opt_fail(bbmpc_opt* o, int code, const char* msg) { return fail(o->ctx, code, "%s", msg); }
+
+template <typename T>
+int dalloc(bbmpc_opt* o, T** p, size_t n) {
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+  if (e != cudaSuccess) return fail(o->ctx, BBMPC_ENOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+  o->owned.push_back(*p);
+  return BBMPC_OK;
+}
+
+// ============================================================================ kernels
+// ---- fills / small vector ops
+__global__ void fill_midpoint_kernel(float* out, const float* lb, const float* ub, int n, int dU) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __fdiv_rn(__fadd_rn(lb[i % dU], ub[i % dU]), 2.0f);   // (lb + ub) / 2
+}
+__global__ void fill_var0_kernel(float* out, const float* lb, const float* ub, int n, int dU) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float d = __fsub_rn(lb[i % dU], ub[i % dU]); out[i] = __fdiv_rn(__fmul_rn(d, d), 16.0f); }
+}
+__global__ void fill_kernel(float* out, float v, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
+// out[a,h,:] = in[a,min(h+1,H-1),:]   (pi2.py:92-93, spsa.py:114-115)
+__global__ void shift_left_kernel(const float* in, float* out, int A, int H, int dU) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A * H * dU) return;
+  const int u = i % dU, h = (i / dU) % H, a = i / (dU * H);
+  const int hs = h + 1 < H ? h + 1 : H - 1;
+  out[i] = in[(a * H + hs) * dU + u];
+}
+// action[a,:] = sol[a,0,:]  (+ exploration noise and clip, optimizer_base.py:82-90)
+__global__ void first_action_kernel(const float* sol, float* action, const float* lb, const float* ub, int A,
+                                    int H, int dU, int sol_stride_a, int add_noise, uint64_t seed, uint32_t act_call) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A * dU) return;
+  const int a = i / dU, u = i % dU;
+  float v = sol[a * sol_stride_a + u];
+  if (add_noise) {
+    const Philox4 r = draw_block(seed, act_call, STREAM_EXPLORE, 0, a, u);
+    const float d = __fsub_rn(lb[u], ub[u]);
+    const float var = __fmul_rn(__fdiv_rn(__fmul_rn(d, d), 16.0f), 0.05f);
+    const float mean = __fdiv_rn(__fadd_rn(ub[u], lb[u]), 2.0f);
+    const float noise = __fadd_rn(__fmul_rn(std_truncnorm(r.x), sqrtf(var)), mean);
+    v = fminf(fmaxf(__fadd_rn(v, noise), lb[u]), ub[u]);
+  }
+  action[i] = v;
+}
+
+// ---- samplers.  One thread per 4 consecutive elements of a (population row, agent) sequence.
+// Global Philox row = p_global * A + a.
+struct SampleArgs {
+  float* samples; float* penalty; const float* mean; const float* var; const float* lb; const float* ub;
+  int P_local, p0, A, H, dU; uint64_t seed; uint32_t act_call, iter;
+  float ck;   // SPSA perturbation size
+};
+
+// cem.py:81-94: cvar = min(((mean-lb)/2)^2, ((ub-mean)/2)^2, var); x = mean + sqrt(cvar)*tn
+__global__ void cem_sample_kernel(const SampleArgs s) {
+  const int HU = s.H * s.dU, nb = (HU + 3) / 4;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<int64_t>(s.P_local) * s.A * nb) return;
+  const int blk = gid % nb; const int64_t pa = gid / nb;
+  const int a = pa % s.A; const int p = pa / s.A;
+  const Philox4 r = draw_block(s.seed, s.act_call, STREAM_SAMPLES, s.iter, (s.p0 + p) * s.A + a, blk);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  for (int j = 0; j < 4; ++j) {
+    const int e = 4 * blk + j;
+    if (e >= HU) break;
+    const int u = e % s.dU;
+    const float m = s.mean[a * HU + e];
+    const float lo = __fdiv_rn(__fsub_rn(m, s.lb[u]), 2.0f), hi = __fdiv_rn(__fsub_rn(s.ub[u], m), 2.0f);
+    const float cvar = fminf(fminf(__fmul_rn(lo, lo), __fmul_rn(hi, hi)), s.var[a * HU + e]);
+    s.samples[pa * HU + e] = __fadd_rn(__fmul_rn(std_truncnorm(w[j]), sqrtf(cvar)), m);
+  }
+}
+// pi2.py:65-76: x = mean + sqrt(var)*tn; clip; penalty[p,a] = ||x - clip(x)||^2 (summed by a
+// second kernel in a fixed order).  Writes the CLIPPED sample and the raw excess^2 into `penalty`
+// scratch laid out like samples?  No: excess is accumulated per (p,a) by penalty_kernel below.
+__global__ void pi2_sample_kernel(const SampleArgs s, float* raw_excess_sq) {
+  const int HU = s.H * s.dU, nb = (HU + 3) / 4;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<int64_t>(s.P_local) * s.A * nb) return;
+  const int blk = gid % nb; const int64_t pa = gid / nb;
+  const int a = pa % s.A; const int p = pa / s.A;
+  const Philox4 r = draw_block(s.seed, s.act_call, STREAM_SAMPLES, s.iter, (s.p0 + p) * s.A + a, blk);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  for (int j = 0; j < 4; ++j) {
+    const int e = 4 * blk + j;
+    if (e >= HU) break;
+    const int u = e % s.dU;
+    const float x = __fadd_rn(__fmul_rn(std_truncnorm(w[j]), sqrtf(s.var[a * HU + e])), s.mean[a * HU + e]);
+    const float xf = fminf(fmaxf(x, s.lb[u]), s.ub[u]);
+    const float d = __fsub_rn(x, xf);
+    s.samples[pa * HU + e] = xf;
+    raw_excess_sq[pa * HU + e] = __fmul_rn(d, d);
+  }
+}
+// random_search.py:40-41: x = lb + (ub - lb) * U[0,1)
+__global__ void rs_sample_kernel(const SampleArgs s) {
+  const int HU = s.H * s.dU, nb = (HU + 3) / 4;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<int64_t>(s.P_local) * s.A * nb) return;
+  const int blk = gid % nb; const int64_t pa = gid / nb;
+  const int a = pa % s.A; const int p = pa / s.A;
+  const Philox4 r = draw_block(s.seed, s.act_call, STREAM_SAMPLES, s.iter, (s.p0 + p) * s.A + a, blk);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  for (int j = 0; j < 4; ++j) {
+    const int e = 4 * blk + j;
+    if (e >= HU) break;
+    const int u = e % s.dU;
+    s.samples[pa * HU + e] = __fadd_rn(__fmul_rn(u01_halfopen(w[j]), __fsub_rn(s.ub[u], s.lb[u])), s.lb[u]);
+  }
+}
+// spsa.py:73-91: delta = +-1; theta+- = sol +- ck*delta; clip; excess^2 (plus rows first, then minus)
+__global__ void spsa_sample_kernel(const SampleArgs s, float* raw_excess_sq) {
+  const int HU = s.H * s.dU, nb = (HU + 3) / 4;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t half = static_cast<int64_t>(s.P_local) * s.A;
+  if (gid >= half * nb) return;
+  const int blk = gid % nb; const int64_t pa = gid / nb;
+  const int a = pa % s.A; const int p = pa / s.A;
+  const Philox4 r = draw_block(s.seed, s.act_call, STREAM_SAMPLES, s.iter, (s.p0 + p) * s.A + a, blk);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  for (int j = 0; j < 4; ++j) {
+    const int e = 4 * blk + j;
+    if (e >= HU) break;
+    const int u = e % s.dU;
+    const float delta = (w[j] >> 31) ? 1.0f : -1.0f;
+    const float step = __fmul_rn(s.ck, delta), m = s.mean[a * HU + e];
+    const float xp = __fadd_rn(m, step), xm = __fsub_rn(m, step);
+    const float xpf = fminf(fmaxf(xp, s.lb[u]), s.ub[u]), xmf = fminf(fmaxf(xm, s.lb[u]), s.ub[u]);
+    s.samples[pa * HU + e] = xpf;
+    s.samples[(half + pa) * HU + e] = xmf;
+    const float dp = __fsub_rn(xp, xpf), dm = __fsub_rn(xm, xmf);
+    raw_excess_sq[pa * HU + e] = __fmul_rn(dp, dp);
+    raw_excess_sq[(half + pa) * HU + e] = __fmul_rn(dm, dm);
+  }
+}
+// penalty[row] = (sqrt(sum_e excess_sq[row,e]))^2 — tf.norm(...,axis=2)**2 [TF]; one warp per row,
+// fixed summation order.
+__global__ void penalty_kernel(const float* excess_sq, float* penalty, int64_t rows, int HU) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float acc = 0.0f;
+  for (int e = lane; e < HU; e += 32) acc += excess_sq[row * HU + e];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) { const float n = sqrtf(acc); penalty[row] = __fmul_rn(n, n); }
+}
+
+// ---- CEM local top-E -> partial message.  One CTA per agent.
+// partial layout per agent: E records of (reward, global_p bits, seq[HU]).
+__global__ void __launch_bounds__(SEL_THREADS) topk_partial_kernel(const float* returns, const float* samples,
+                                                                   float* partial, int P_local, int p0, int A,
+                                                                   int HU, int E) {
+  __shared__ int hist[256];
+  __shared__ int misc[40];
+  __shared__ uint32_t keys[SEL_MAX_K];
+  __shared__ int idx[SEL_MAX_K];
+  const int a = blockIdx.x;
+  const SelectScratch sc{hist, misc, keys, idx};
+  block_topk(returns + a, P_local, A, E, sc);
+  const int rec = 2 + HU;
+  float* out = partial + static_cast<size_t>(a) * E * rec;
+  for (int i = threadIdx.x; i < E * rec; i += SEL_THREADS) {
+    const int r = i / rec, c = i % rec;
+    const int p = idx[r];
+    const bool ok = p != 0x7FFFFFFF;
+    float v;
+    if (c == 0) v = ok ? key2f(keys[r]) : -INFINITY;
+    else if (c == 1) v = __int_as_float(ok ? p0 + p : 0x7FFFFFFF);
+    else v = ok ? samples[(static_cast<size_t>(p) * A + a) * HU + (c - 2)] : 0.0f;
+    out[i] = v;
+  }
+}
+
+// ---- CEM merge + refit (cem.py:98-125).  One CTA per agent; candidates = world x E records.
+__global__ void __launch_bounds__(SEL_THREADS) cem_refit_kernel(const float* partials, int world, int A, int HU,
+                                                                int E, float alpha, float* mean, float* var,
+                                                                int64_t partial_stride) {
+  __shared__ uint32_t keys[SEL_MAX_K];
+  __shared__ int gp[SEL_MAX_K];
+  __shared__ int src[SEL_MAX_K];
+  const int a = blockIdx.x, rec = 2 + HU, n = world * E;
+  int n2 = 1; while (n2 < n) n2 <<= 1;
+  // sort candidates by (reward desc, global p asc); `src` carries the candidate slot along.
+  for (int i = threadIdx.x; i < n2; i += SEL_THREADS) {
+    if (i < n) {
+      const float* r = partials + (i / E) * partial_stride + (static_cast<size_t>(a) * E + (i % E)) * rec;
+      keys[i] = f2key(r[0]); gp[i] = __float_as_int(r[1]);
+    } else { keys[i] = 0u; gp[i] = 0x7FFFFFFF; }
+  }
+  __syncthreads();
+  if (world > 1) {
+    // rank the candidates: position = number of candidates strictly before it (n <= 1024, O(n^2/threads))
+    for (int i = threadIdx.x; i < n; i += SEL_THREADS) {
+      int pos = 0;
+      for (int j = 0; j < n; ++j) pos += before(keys[j], gp[j], keys[i], gp[i]) ? 1 : 0;
+      src[pos] = i;
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += SEL_THREADS) src[i] = i;  // local list is already sorted
+  }
+  __syncthreads();
+  // elites = first E in order; mean, ddof-0 variance in elite order; alpha blend
+  for (int e = threadIdx.x; e < HU; e += SEL_THREADS) {
+    float sum = 0.0f;
+    for (int k = 0; k < E; ++k) {
+      const int i = src[k];
+      sum += partials[(i / E) * partial_stride + (static_cast<size_t>(a) * E + (i % E)) * rec + 2 + e];
+    }
+    const float nm = __fdiv_rn(sum, static_cast<float>(E));
+    float sq = 0.0f;
+    for (int k = 0; k < E; ++k) {
+      const int i = src[k];
+      const float d = __fsub_rn(partials[(i / E) * partial_stride + (static_cast<size_t>(a) * E + (i % E)) * rec + 2 + e], nm);
+      sq += __fmul_rn(d, d);
+    }
+    const float nv = __fdiv_rn(sq, static_cast<float>(E));
+    const float one_m = __fsub_rn(1.0f, alpha);
+    mean[a * HU + e] = __fadd_rn(__fmul_rn(alpha, mean[a * HU + e]), __fmul_rn(one_m, nm));
+    var[a * HU + e] = __fadd_rn(__fmul_rn(alpha, var[a * HU + e]), __fmul_rn(one_m, nv));
+  }
+}
+
+// ---- PI2 local partial (pi2.py:79-87): per agent (max_r, sum e, sum e*x[HU]), e = exp((r - max_r)/lambda)
+__global__ void __launch_bounds__(1024) pi2_partial_kernel(const float* returns, const float* samples, float* partial,
+                                                           int P_local, int A, int HU, float lamda) {
+  __shared__ float red[32];
+  __shared__ float s_max, s_sum;
+  const int a = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float mx = -INFINITY;
+  for (int p = tid; p < P_local; p += 1024) mx = fmaxf(mx, returns[p * A + a]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    mx = red[lane];
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_max = mx;
+  }
+  __syncthreads();
+  mx = s_max;
+  const float inv_l = __fdiv_rn(1.0f, lamda);
+  float sm = 0.0f;
+  for (int p = tid; p < P_local; p += 1024) sm += expf(-inv_l * ((-returns[p * A + a]) - (-mx)));
+  for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = sm;
+  __syncthreads();
+  if (warp == 0) {
+    sm = red[lane];
+    for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+    if (lane == 0) s_sum = sm;
+  }
+  __syncthreads();
+  float* out = partial + static_cast<size_t>(a) * (2 + HU);
+  if (tid == 0) { out[0] = mx; out[1] = s_sum; }
+  // weighted sums: warp w handles elements e = w, w+32, ...; lanes stride the population
+  for (int e = warp; e < HU; e += 32) {
+    float acc = 0.0f;
+    for (int p = lane; p < P_local; p += 32) {
+      const float wgt = expf(-inv_l * ((-returns[p * A + a]) - (-mx)));
+      acc = fmaf(wgt, samples[(static_cast<size_t>(p) * A + a) * HU + e], acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[2 + e] = acc;
+  }
+}
+// PI2 merge: log-sum-exp combination of the ranks' partials -> new mean (pi2.py:80-87)
+__global__ void pi2_merge_kernel(const float* partials, int world, int A, int HU, float lamda, float* mean,
+                                 int64_t partial_stride) {
+  const int a = blockIdx.x;
+  const int rec = 2 + HU;
+  float gmax = -INFINITY;
+  for (int g = 0; g < world; ++g) gmax = fmaxf(gmax, partials[g * partial_stride + a * rec]);
+  const float inv_l = __fdiv_rn(1.0f, lamda);
+  float eta = 0.0f;
+  for (int g = 0; g < world; ++g) {
+    const float* r = partials + g * partial_stride + a * rec;
+    eta += r[1] * expf(-inv_l * (gmax - r[0]));
+  }
+  for (int e = threadIdx.x; e < HU; e += blockDim.x) {
+    float acc = 0.0f;
+    for (int g = 0; g < world; ++g) {
+      const float* r = partials + g * partial_stride + a * rec;
+      acc += r[2 + e] * expf(-inv_l * (gmax - r[0]));
+    }
+    mean[a * HU + e] = __fmul_rn(__fdiv_rn(1.0f, eta), acc);
+  }
+}
+
+// ---- RandomSearch / PSO: local argmax over the population (first index wins) -> (value, global p, seq[HU])
+__global__ void __launch_bounds__(1024) argmax_partial_kernel(const float* vals, const float* seqs, float* partial,
+                                                              int P_local, int p0, int A, int HU) {
+  __shared__ uint32_t s_key[32];
+  __shared__ int s_idx[32];
+  const int a = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t bk = 0; int bi = 0x7FFFFFFF;
+  for (int p = tid; p < P_local; p += 1024) {
+    const uint32_t k = f2key(vals[p * A + a]);
+    if (before(k, p, bk, bi)) { bk = k; bi = p; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint32_t ok = __shfl_xor_sync(0xffffffffu, bk, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (before(ok, oi, bk, bi)) { bk = ok; bi = oi; }
+  }
+  if (lane == 0) { s_key[warp] = bk; s_idx[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    bk = s_key[lane]; bi = s_idx[lane];
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint32_t ok = __shfl_xor_sync(0xffffffffu, bk, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (before(ok, oi, bk, bi)) { bk = ok; bi = oi; }
+    }
+    if (lane == 0) { s_key[0] = bk; s_idx[0] = bi; }
+  }
+  __syncthreads();
+  bk = s_key[0]; bi = s_idx[0];
+  float* out = partial + static_cast<size_t>(a) * (2 + HU);
+  const bool ok = bi != 0x7FFFFFFF;
+  if (tid == 0) { out[0] = ok ? key2f(bk) : -INFINITY; out[1] = __int_as_float(ok ? p0 + bi : 0x7FFFFFFF); }
+  for (int e = tid; e < HU; e += 1024) out[2 + e] = ok ? seqs[(static_cast<size_t>(bi) * A + a) * HU + e] : 0.0f;
+}
+// merge: best record over ranks (value desc, global p asc) -> best_seq[a,:], best_val[a]
+__global__ void argmax_merge_kernel(const float* partials, int world, int HU, float* best_seq, float* best_val,
+                                    int64_t partial_stride) {
+  const int a = blockIdx.x, rec = 2 + HU;
+  int bg = 0; uint32_t bk = 0; int bi = 0x7FFFFFFF;
+  for (int g = 0; g < world; ++g) {
+    const float* r = partials + g * partial_stride + a * rec;
+    const uint32_t k = f2key(r[0]); const int i = __float_as_int(r[1]);
+    if (g == 0 || before(k, i, bk, bi)) { bk = k; bi = i; bg = g; }
+  }
+  const float* r = partials + bg * partial_stride + a * rec;
+  for (int e = threadIdx.x; e < HU; e += blockDim.x) best_seq[a * HU + e] = r[2 + e];
+  if (threadIdx.x == 0 && best_val) best_val[a] = r[0];
+}
+
+// ---- SPSA partial: sum_p (r+ - r-) / (2 ck delta) per (a,e) (spsa.py:98-103); delta regenerated
+__global__ void spsa_partial_kernel(const float* returns, float* partial, int P_local, int p0, int A, int HU,
+                                    float ck, uint64_t seed, uint32_t act_call, uint32_t iter) {
+  // one warp per (a, e): lanes stride the population, fixed-order tree reduction
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= A * HU) return;
+  const int a = w / HU, e = w % HU;
+  const int64_t half = static_cast<int64_t>(P_local) * A;
+  float acc = 0.0f;
+  for (int p = lane; p < P_local; p += 32) {
+    const Philox4 r = draw_block(seed, act_call, STREAM_SAMPLES, iter, (p0 + p) * A + a, e >> 2);
+    const uint32_t word = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
+    const float delta = (word >> 31) ? 1.0f : -1.0f;
+    const float diff = __fsub_rn(returns[p * A + a], returns[half + p * A + a]);
+    acc += __fdiv_rn(diff, __fmul_rn(__fmul_rn(2.0f, ck), delta));
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) partial[w] = acc;
+}
+// SPSA merge (spsa.py:101-107): ghat = sum / P; sol = clip(sol + ak * ghat)
+__global__ void spsa_merge_kernel(const float* partials, int world, int n, int P, float ak, float* sol,
+                                  const float* lb, const float* ub, int dU, int64_t partial_stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int g = 0; g < world; ++g) s += partials[g * partial_stride + i];
+  const float ghat = __fdiv_rn(s, static_cast<float>(P));
+  const float v = __fadd_rn(sol[i], __fmul_rn(ak, ghat));
+  sol[i] = fminf(fmaxf(v, lb[i % dU]), ub[i % dU]);
+}
+
+// ---- PSO (pso.py:79-111)
+// clip + excess^2 in place, before evaluation
+__global__ void pso_clip_kernel(float* x, float* excess_sq, const float* lb, const float* ub, int64_t n, int dU) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i], f = fminf(fmaxf(v, lb[i % dU]), ub[i % dU]);
+  const float d = __fsub_rn(v, f);
+  x[i] = f; excess_sq[i] = __fmul_rn(d, d);
+}
+// personal best update (pso.py:87-94): where pbest_r < reward
+__global__ void pso_pbest_kernel(const float* x, const float* rewards, float* pbx, float* pbr, int64_t rows, int HU) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * HU) return;
+  const int64_t row = i / HU;
+  if (pbr[row] < rewards[row]) pbx[i] = x[i];
+}
+__global__ void pso_pbest_r_kernel(const float* rewards, float* pbr, int64_t rows) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < rows && pbr[i] < rewards[i]) pbr[i] = rewards[i];
+}
+// velocity / position update (pso.py:107-111); r1, r2: ONE N(0,1) scalar each per iteration
+__global__ void pso_move_kernel(float* x, float* v, const float* pbx, const float* gbx, int64_t n, int AHU, float w,
+                                float c1, float c2, uint64_t seed, uint32_t act_call, uint32_t iter) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Philox4 r = draw_block(seed, act_call, STREAM_PSO_R, iter, 0, 0);
+  const float r1 = std_normal(r.x), r2 = std_normal(r.y);
+  const float xi = x[i];
+  const float nv = __fadd_rn(__fadd_rn(__fmul_rn(v[i], w), __fmul_rn(__fmul_rn(__fsub_rn(pbx[i], xi), c1), r1)),
+                             __fmul_rn(__fmul_rn(__fsub_rn(gbx[i % AHU], xi), c2), r2));
+  v[i] = nv;
+  x[i] = __fadd_rn(xi, nv);
+}
+// swarm (re-)seeding: mode 0 = reset() uniform positions (pso.py:147-159); mode 1 = the tail of
+// _optimize: x ~ truncnorm(shift(gbest), sqrt(cvar(UNSHIFTED gbest))) (pso.py:116-138)
+__global__ void pso_seed_kernel(float* x, float* v, float* pbx, const float* gbx, const float* var0, const float* lb,
+                                const float* ub, int P_local, int p0, int A, int H, int dU, float v0frac, int mode,
+                                uint64_t seed, uint32_t act_call) {
+  const int HU = H * dU;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(P_local) * A * HU) return;
+  const int e = i % HU; const int64_t pa = i / HU; const int a = pa % A; const int p = pa / A;
+  const int u = e % dU, h = e / dU;
+  const uint32_t row = (p0 + p) * A + a;
+  const Philox4 rp = draw_block(seed, act_call, STREAM_PSO_POS, mode, row, e >> 2);
+  const Philox4 rv = draw_block(seed, act_call, STREAM_PSO_VEL, mode, row, e >> 2);
+  const uint32_t wp = (e & 3) == 0 ? rp.x : (e & 3) == 1 ? rp.y : (e & 3) == 2 ? rp.z : rp.w;
+  const uint32_t wv = (e & 3) == 0 ? rv.x : (e & 3) == 1 ? rv.y : (e & 3) == 2 ? rv.z : rv.w;
+  float pos;
+  if (mode == 0) {
+    pos = __fadd_rn(__fmul_rn(u01_halfopen(wp), __fsub_rn(ub[u], lb[u])), lb[u]);
+  } else {
+    const float g = gbx[a * HU + e];
+    const int hs = h + 1 < H ? h + 1 : H - 1;
+    const float gs = gbx[a * HU + hs * dU + u];
+    const float lo = __fdiv_rn(__fsub_rn(g, lb[u]), 2.0f), hi = __fdiv_rn(__fsub_rn(ub[u], g), 2.0f);
+    const float cvar = fminf(fminf(__fmul_rn(lo, lo), __fmul_rn(hi, hi)), var0[a * HU + e]);
+    pos = __fadd_rn(__fmul_rn(std_truncnorm(wp), sqrtf(cvar)), gs);
+  }
+  const float v0 = __fmul_rn(v0frac, __fsub_rn(ub[u], lb[u]));
+  const float vel = __fadd_rn(__fmul_rn(u01_halfopen(wv), __fsub_rn(v0, -v0)), -v0);
+  x[i] = pos; pbx[i] = pos; v[i] = vel;
+}
+
+inline int grid_for(int64_t n, int block) { return static_cast<int>((n + block - 1) / block); }
+
+}  // namespace
+
+// ============================================================================ host orchestration
+static int partial_floats(const bbmpc_opt* o) {
+  const int A = o->cfg.num_agents, HU = o->HU;
+  switch (o->cfg.kind) {
+    case BBMPC_OPT_CEM: return A * o->cfg.num_elite * (2 + HU);
+    case BBMPC_OPT_PI2: return A * (2 + HU);
+    case BBMPC_OPT_RANDOM_SEARCH: return A * (2 + HU);
+    case BBMPC_OPT_PSO: return A * (2 + HU);
+    case BBMPC_OPT_SPSA: return A * HU;
+    default: return 0;
+  }
+}
+
+static int set_shard(bbmpc_opt* o, int rank, int world);
+
+extern "C" {
+
+int bbmpc_opt_create(bbmpc_ctx* ctx, const bbmpc_opt_config* cfg, bbmpc_opt** out) {
+  if (!ctx || !cfg || !out) return BBMPC_EINVAL;
+  *out = nullptr;
+  const int P = cfg->population_size, A = cfg->num_agents, H = cfg->planning_horizon, dU = cfg->dU, dS = cfg->dS;
+  if (cfg->kind < BBMPC_OPT_CEM || cfg->kind > BBMPC_OPT_CMAES) return fail(ctx, BBMPC_EINVAL, "unknown optimizer kind %d", cfg->kind);
+  if (cfg->kind == BBMPC_OPT_CMAES) return fail(ctx, BBMPC_EINVAL, "CMA-ES refit is not built into libbbmpc yet");
+  if (P < 1 || A < 1 || H < 1 || dU < 1 || dS < 1 || dU > MAX_DU || dS > MAX_DS)
+    return fail(ctx, BBMPC_EINVAL, "bad optimizer shape P=%d A=%d H=%d dS=%d dU=%d", P, A, H, dS, dU);
+  if (!cfg->lb_host || !cfg->ub_host) return fail(ctx, BBMPC_EINVAL, "action bounds missing");
+  if (cfg->kind != BBMPC_OPT_RANDOM_SEARCH && cfg->max_iterations < 0) return fail(ctx, BBMPC_EINVAL, "max_iterations < 0");
+  if (cfg->kind == BBMPC_OPT_CEM && (cfg->num_elite < 1 || cfg->num_elite > P || cfg->num_elite > SEL_MAX_K))
+    return fail(ctx, BBMPC_EINVAL, "num_elite=%d must be in [1, min(P, %d)]", cfg->num_elite, SEL_MAX_K);
+  if (ctx->model.set && (ctx->model.dS != dS || ctx->model.dU != dU))
+    return fail(ctx, BBMPC_EINVAL, "optimizer dS=%d dU=%d differ from the model's dS=%d dU=%d", dS, dU, ctx->model.dS, ctx->model.dU);
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  bbmpc_opt* o = new bbmpc_opt();
+  o->ctx = ctx; o->cfg = *cfg; o->cfg.lb_host = nullptr; o->cfg.ub_host = nullptr;
+  o->HU = H * dU; o->AHU = A * H * dU;
+  int rc = BBMPC_OK;
+  auto A_ = [&](int r) { if (rc == BBMPC_OK) rc = r; };
+  A_(dalloc(o, &o->d_lb, dU)); A_(dalloc(o, &o->d_ub, dU));
+  A_(dalloc(o, &o->d_state, A * dS)); A_(dalloc(o, &o->d_mean, o->AHU)); A_(dalloc(o, &o->d_var, o->AHU));
+  A_(dalloc(o, &o->d_prev, o->AHU)); A_(dalloc(o, &o->d_var0, o->AHU));
+  A_(dalloc(o, &o->d_action, A * dU)); A_(dalloc(o, &o->d_next, A * dS)); A_(dalloc(o, &o->d_reward, A));
+  if (cfg->kind == BBMPC_OPT_PSO) { A_(dalloc(o, &o->d_gbx, o->AHU)); A_(dalloc(o, &o->d_gbr, A)); A_(dalloc(o, &o->d_sol, A * dU)); }
+  if (rc == BBMPC_OK && cudaMallocHost(reinterpret_cast<void**>(&o->h_pinned), (A * dS * 2 + A * dU + A) * sizeof(float)) != cudaSuccess)
+    rc = fail(ctx, BBMPC_ENOMEM, "cudaMallocHost failed");
+  if (rc != BBMPC_OK) { bbmpc_opt_destroy(o); return rc; }
+  cudaMemcpy(o->d_lb, cfg->lb_host, dU * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemcpy(o->d_ub, cfg->ub_host, dU * sizeof(float), cudaMemcpyHostToDevice);
+  fill_midpoint_kernel<<<grid_for(o->AHU, 256), 256>>>(o->d_prev, o->d_lb, o->d_ub, o->AHU, dU);
+  fill_var0_kernel<<<grid_for(o->AHU, 256), 256>>>(o->d_var0, o->d_lb, o->d_ub, o->AHU, dU);
+  ctx->launches += 2;
+  if (cfg->kind == BBMPC_OPT_PSO) {  // every tf.Variable starts at zero (pso.py:50-68)
+    cudaMemset(o->d_gbx, 0, o->AHU * sizeof(float)); cudaMemset(o->d_gbr, 0, A * sizeof(float));
+    cudaMemset(o->d_sol, 0, A * dU * sizeof(float));
+  }
+  if ((rc = set_shard(o, 0, 1)) != BBMPC_OK) { bbmpc_opt_destroy(o); return rc; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { rc = fail(ctx, BBMPC_ECUDA, "optimizer init: %s", cudaGetErrorString(e)); bbmpc_opt_destroy(o); return rc; }
+  *out = o;
+  return BBMPC_OK;
+}
+
+void bbmpc_opt_destroy(bbmpc_opt* o) {
+  if (!o) return;
+  cudaSetDevice(o->ctx->device);
+  cudaDeviceSynchronize();
+  for (void* p : o->owned) cudaFree(p);
+  if (o->h_pinned) cudaFreeHost(o->h_pinned);
+  delete o;
+}
+
+}  // extern "C"
+
+// (Re)allocates the population-sized buffers for this rank's slice.
+static int set_shard(bbmpc_opt* o, int rank, int world) {
+  bbmpc_ctx* ctx = o->ctx;
+  const int P = o->cfg.population_size, A = o->cfg.num_agents;
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, BBMPC_EINVAL, "bad shard %d/%d", rank, world);
+  if (world > 1 && o->cfg.kind == BBMPC_OPT_CEM && world * o->cfg.num_elite > SEL_MAX_K)
+    return fail(ctx, BBMPC_EINVAL, "world*num_elite = %d exceeds %d", world * o->cfg.num_elite, SEL_MAX_K);
+  BB_CUDA(ctx, cudaDeviceSynchronize());
+  o->rank = rank; o->world = world;
+  o->p0 = static_cast<int>(static_cast<int64_t>(P) * rank / world);
+  o->P_local = static_cast<int>(static_cast<int64_t>(P) * (rank + 1) / world) - o->p0;
+  o->n_eval = o->cfg.kind == BBMPC_OPT_SPSA ? 2 * o->P_local : o->P_local;
+  const size_t rows = static_cast<size_t>(o->n_eval) * A;
+  int rc = BBMPC_OK;
+  auto A_ = [&](int r) { if (rc == BBMPC_OK) rc = r; };
+  // (old population buffers stay in `owned` until destroy; resharding is a setup-time operation)
+  A_(dalloc(o, &o->d_samples, rows * o->HU)); A_(dalloc(o, &o->d_returns, rows)); A_(dalloc(o, &o->d_penalty, rows));
+  A_(dalloc(o, &o->d_partial, static_cast<size_t>(partial_floats(o))));
+  if (o->cfg.kind == BBMPC_OPT_PI2 || o->cfg.kind == BBMPC_OPT_SPSA || o->cfg.kind == BBMPC_OPT_PSO)
+    A_(dalloc(o, &o->d_work, rows * o->HU));
+  if (o->cfg.kind == BBMPC_OPT_PSO) {
+    A_(dalloc(o, &o->d_v, rows * o->HU)); A_(dalloc(o, &o->d_pbx, rows * o->HU)); A_(dalloc(o, &o->d_pbr, rows));
+    if (rc == BBMPC_OK) {
+      cudaMemset(o->d_samples, 0, rows * o->HU * sizeof(float)); cudaMemset(o->d_v, 0, rows * o->HU * sizeof(float));
+      cudaMemset(o->d_pbx, 0, rows * o->HU * sizeof(float)); cudaMemset(o->d_pbr, 0, rows * sizeof(float));
+    }
+  }
+  return rc;
+}
+
+extern "C" {
+
+int bbmpc_opt_set_shard(bbmpc_opt* o, int rank, int world) {
+  if (!o) return BBMPC_EINVAL;
+  BB_CUDA(o->ctx, cudaSetDevice(o->ctx->device));
+  return set_shard(o, rank, world);
+}
+
+int bbmpc_opt_num_iterations(const bbmpc_opt* o) {
+  if (!o) return BBMPC_EINVAL;
+  return o->cfg.kind == BBMPC_OPT_RANDOM_SEARCH ? 1 : o->cfg.max_iterations;
+}
+int bbmpc_opt_partial_floats(const bbmpc_opt* o) { return o ? partial_floats(o) : BBMPC_EINVAL; }
+
+int bbmpc_opt_reset(bbmpc_opt* o, void* stream) {
+  if (!o) return BBMPC_EINVAL;
+  bbmpc_ctx* ctx = o->ctx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int dU = o->cfg.dU;
+  switch (o->cfg.kind) {
+    case BBMPC_OPT_CEM: case BBMPC_OPT_PI2: case BBMPC_OPT_SPSA:  // mean/params back to the midpoint only
+      fill_midpoint_kernel<<<grid_for(o->AHU, 256), 256, 0, st>>>(o->d_prev, o->d_lb, o->d_ub, o->AHU, dU);
+      BB_LAUNCH_CHECK(ctx);
+      break;
+    case BBMPC_OPT_PSO: {
+      const int64_t n = static_cast<int64_t>(o->P_local) * o->AHU;
+      pso_seed_kernel<<<grid_for(n, 256), 256, 0, st>>>(o->d_samples, o->d_v, o->d_pbx, o->d_gbx, o->d_var0, o->d_lb, o->d_ub,
+                                                        o->P_local, o->p0, o->cfg.num_agents, o->cfg.planning_horizon, dU,
+                                                        o->cfg.initial_velocity_fraction, 0, ctx->seed, o->act_call);
+      BB_LAUNCH_CHECK(ctx);
+      const int64_t rows = static_cast<int64_t>(o->P_local) * o->cfg.num_agents;
+      fill_kernel<<<grid_for(rows, 256), 256, 0, st>>>(o->d_pbr, -INFINITY, rows); BB_LAUNCH_CHECK(ctx);
+      fill_kernel<<<1, 256, 0, st>>>(o->d_gbr, -INFINITY, o->cfg.num_agents); BB_LAUNCH_CHECK(ctx);
+      o->act_call++;  // a reset consumes its own Philox sub-stream
+      break;
+    }
+    default: break;  // RandomSearch: nothing
+  }
+  return BBMPC_OK;
+}
+
+int bbmpc_opt_begin(bbmpc_opt* o, const float* state, int time_step, void* stream) {
+  if (!o) return BBMPC_EINVAL;
+  bbmpc_ctx* ctx = o->ctx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!state) return opt_fail(o, BBMPC_EINVAL, "state is NULL");
+  if (!ctx->model.set) return opt_fail(o, BBMPC_ESTATE, "optimizer called before a dynamics model was set");
+  if (!ctx->reward_id) return opt_fail(o, BBMPC_ESTATE, "optimizer called before a reward function was set");
+  if (ctx->model.dS != o->cfg.dS || ctx->model.dU != o->cfg.dU) return opt_fail(o, BBMPC_EINVAL, "optimizer/model dS,dU mismatch");
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  o->time_step = time_step;  // accepted and ignored, as in deterministic.py:26
+  if (state != o->d_state)
+    BB_CUDA(ctx, cudaMemcpyAsync(o->d_state, state, o->cfg.num_agents * o->cfg.dS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  switch (o->cfg.kind) {
+    case BBMPC_OPT_CEM:  // loop_vars = [_previous_solution, _solution_variance] (cem.py:129-132)
+      BB_CUDA(ctx, cudaMemcpyAsync(o->d_mean, o->d_prev, o->AHU * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      BB_CUDA(ctx, cudaMemcpyAsync(o->d_var, o->d_var0, o->AHU * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      break;
+    case BBMPC_OPT_PI2: case BBMPC_OPT_SPSA:
+      BB_CUDA(ctx, cudaMemcpyAsync(o->d_mean, o->d_prev, o->AHU * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      break;
+    default: break;
+  }
+  o->began = true;
+  return BBMPC_OK;
+}
+
+int bbmpc_opt_iter_local(bbmpc_opt* o, int iter, float* partial_out, void* stream) {
+  if (!o) return BBMPC_EINVAL;
+  bbmpc_ctx* ctx = o->ctx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!o->began) return opt_fail(o, BBMPC_ESTATE, "iter_local before begin");
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bbmpc_opt_config& c = o->cfg;
+  const int A = c.num_agents, H = c.planning_horizon, dU = c.dU, HU = o->HU;
+  float* partial = partial_out ? partial_out : o->d_partial;
+  SampleArgs s{o->d_samples, o->d_penalty, o->d_mean, o->d_var, o->d_lb, o->d_ub, o->P_local, o->p0, A, H, dU,
+               ctx->seed, o->act_call, static_cast<uint32_t>(iter), 0.0f};
+  const int64_t rows = static_cast<int64_t>(o->n_eval) * A;
+  const int64_t nthr = static_cast<int64_t>(o->P_local) * A * ((HU + 3) / 4);
+  const float* penalty = nullptr;
+  if (o->P_local > 0) {
+    switch (c.kind) {
+      case BBMPC_OPT_CEM:
+        cem_sample_kernel<<<grid_for(nthr, 256), 256, 0, st>>>(s); BB_LAUNCH_CHECK(ctx);
+        break;
+      case BBMPC_OPT_PI2:
+        s.var = o->d_var0;
+        pi2_sample_kernel<<<grid_for(nthr, 256), 256, 0, st>>>(s, o->d_work); BB_LAUNCH_CHECK(ctx);
+        penalty_kernel<<<grid_for(rows * 32, 256), 256, 0, st>>>(o->d_work, o->d_penalty, rows, HU); BB_LAUNCH_CHECK(ctx);
+        penalty = o->d_penalty;
+        break;
+      case BBMPC_OPT_RANDOM_SEARCH:
+        rs_sample_kernel<<<grid_for(nthr, 256), 256, 0, st>>>(s); BB_LAUNCH_CHECK(ctx);
+        break;
+      case BBMPC_OPT_SPSA:
+        s.ck = c.noise_parameter / powf(static_cast<float>(iter) + 1.0f, c.gamma);
+        spsa_sample_kernel<<<grid_for(nthr, 256), 256, 0, st>>>(s, o->d_work); BB_LAUNCH_CHECK(ctx);
+        penalty_kernel<<<grid_for(rows * 32, 256), 256, 0, st>>>(o->d_work, o->d_penalty, rows, HU); BB_LAUNCH_CHECK(ctx);
+        penalty = o->d_penalty;
+        break;
+      case BBMPC_OPT_PSO:
+        pso_clip_kernel<<<grid_for(rows * HU, 256), 256, 0, st>>>(o->d_samples, o->d_work, o->d_lb, o->d_ub, rows * HU, dU); BB_LAUNCH_CHECK(ctx);
+        penalty_kernel<<<grid_for(rows * 32, 256), 256, 0, st>>>(o->d_work, o->d_penalty, rows, HU); BB_LAUNCH_CHECK(ctx);
+        penalty = o->d_penalty;
+        break;
+      default: return opt_fail(o, BBMPC_EINVAL, "unsupported optimizer kind");
+    }
+    if (o->trace) {
+      const int64_t per_iter = rows * HU;
+      if ((static_cast<int64_t>(iter) + 1) * per_iter <= o->trace_floats)
+        BB_CUDA(ctx, cudaMemcpyAsync(o->trace + iter * per_iter, o->d_samples, per_iter * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    if (int rc = rollout_dispatch(ctx, o->d_state, o->d_samples, o->d_returns, penalty, static_cast<int>(rows), A, H, st)) return rc;
+  }
+  switch (c.kind) {
+    case BBMPC_OPT_CEM:
+      topk_partial_kernel<<<A, SEL_THREADS, 0, st>>>(o->d_returns, o->d_samples, partial, o->P_local, o->p0, A, HU, c.num_elite);
+      break;
+    case BBMPC_OPT_PI2:
+      pi2_partial_kernel<<<A, 1024, 0, st>>>(o->d_returns, o->d_samples, partial, o->P_local, A, HU, c.lamda);
+      break;
+    case BBMPC_OPT_RANDOM_SEARCH:
+      argmax_partial_kernel<<<A, 1024, 0, st>>>(o->d_returns, o->d_samples, partial, o->P_local, o->p0, A, HU);
+      break;
+    case BBMPC_OPT_SPSA:
+      spsa_partial_kernel<<<grid_for(static_cast<int64_t>(A) * HU * 32, 256), 256, 0, st>>>(
+          o->d_returns, partial, o->P_local, o->p0, A, HU, c.noise_parameter / powf(static_cast<float>(iter) + 1.0f, c.gamma),
+          ctx->seed, o->act_call, static_cast<uint32_t>(iter));
+      break;
+    case BBMPC_OPT_PSO: {
+      pso_pbest_kernel<<<grid_for(rows * HU, 256), 256, 0, st>>>(o->d_samples, o->d_returns, o->d_pbx, o->d_pbr, rows, HU); BB_LAUNCH_CHECK(ctx);
+      pso_pbest_r_kernel<<<grid_for(rows, 256), 256, 0, st>>>(o->d_returns, o->d_pbr, rows); BB_LAUNCH_CHECK(ctx);
+      argmax_partial_kernel<<<A, 1024, 0, st>>>(o->d_pbr, o->d_pbx, partial, o->P_local, o->p0, A, HU);
+      break;
+    }
+    default: break;
+  }
+  BB_LAUNCH_CHECK(ctx);
+  return BBMPC_OK;
+}
+
+int bbmpc_opt_iter_merge(bbmpc_opt* o, int iter, const float* partials, int world, void* stream) {
+  if (!o) return BBMPC_EINVAL;
+  bbmpc_ctx* ctx = o->ctx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!o->began) return opt_fail(o, BBMPC_ESTATE, "iter_merge before begin");
+  if (world < 1) return opt_fail(o, BBMPC_EINVAL, "world < 1");
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bbmpc_opt_config& c = o->cfg;
+  const int A = c.num_agents, HU = o->HU;
+  const float* in = partials ? partials : o->d_partial;
+  const int64_t stride = partial_floats(o);
+  switch (c.kind) {
+    case BBMPC_OPT_CEM:
+      if (world * c.num_elite > SEL_MAX_K) return opt_fail(o, BBMPC_EINVAL, "world*num_elite exceeds 1024");
+      cem_refit_kernel<<<A, SEL_THREADS, 0, st>>>(in, world, A, HU, c.num_elite, c.alpha, o->d_mean, o->d_var, stride);
+      break;
+    case BBMPC_OPT_PI2:
+      pi2_merge_kernel<<<A, 256, 0, st>>>(in, world, A, HU, c.lamda, o->d_mean, stride);
+      break;
+    case BBMPC_OPT_RANDOM_SEARCH:
+      argmax_merge_kernel<<<A, 256, 0, st>>>(in, world, HU, o->d_mean, nullptr, stride);
+      break;
+    case BBMPC_OPT_SPSA: {
+      const float big_a = static_cast<float>(c.max_iterations) / 10.0f;
+      const float ak = c.a_par / powf(static_cast<float>(iter) + 1.0f + big_a, c.alpha);
+      spsa_merge_kernel<<<grid_for(o->AHU, 256), 256, 0, st>>>(in, world, o->AHU, c.population_size, ak, o->d_mean, o->d_lb, o->d_ub, c.dU, stride);
+      break;
+    }
+    case BBMPC_OPT_PSO: {
+      argmax_merge_kernel<<<A, 256, 0, st>>>(in, world, HU, o->d_gbx, o->d_gbr, stride); BB_LAUNCH_CHECK(ctx);
+      const int64_t n = static_cast<int64_t>(o->P_local) * o->AHU;
+      if (n > 0)
+        pso_move_kernel<<<grid_for(n, 256), 256, 0, st>>>(o->d_samples, o->d_v, o->d_pbx, o->d_gbx, n, o->AHU, c.w, c.c1, c.c2,
+                                                          ctx->seed, o->act_call, static_cast<uint32_t>(iter));
+      else return BBMPC_OK;
+      break;
+    }
+    default: return opt_fail(o, BBMPC_EINVAL, "unsupported optimizer kind");
+  }
+  BB_LAUNCH_CHECK(ctx);
+  return BBMPC_OK;
+}
+
+int bbmpc_opt_finish(bbmpc_opt* o, int add_noise, float* action, float* next_state, float* reward, void* stream) {
+  if (!o) return BBMPC_EINVAL;
+  bbmpc_ctx* ctx = o->ctx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!o->began) return opt_fail(o, BBMPC_ESTATE, "finish before begin");
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bbmpc_opt_config& c = o->cfg;
+  const int A = c.num_agents, H = c.planning_horizon, dU = c.dU, dS = c.dS, HU = o->HU;
+  const float* sol = o->d_mean; int sol_stride = HU;
+  switch (c.kind) {
+    case BBMPC_OPT_PI2: case BBMPC_OPT_SPSA:  // warm start: shift left, repeat last (pi2.py:92-93, spsa.py:114-115)
+      shift_left_kernel<<<grid_for(o->AHU, 256), 256, 0, st>>>(o->d_mean, o->d_prev, A, H, dU); BB_LAUNCH_CHECK(ctx);
+      break;
+    case BBMPC_OPT_PSO: {  // _solution = gbest[:,0,:]; then re-seed the swarm (pso.py:114-138)
+      sol = o->d_gbx;
+      const int64_t n = static_cast<int64_t>(o->P_local) * o->AHU;
+      if (n > 0) {
+        pso_seed_kernel<<<grid_for(n, 256), 256, 0, st>>>(o->d_samples, o->d_v, o->d_pbx, o->d_gbx, o->d_var0, o->d_lb, o->d_ub,
+                                                          o->P_local, o->p0, A, H, dU, c.initial_velocity_fraction, 1, ctx->seed, o->act_call);
+        BB_LAUNCH_CHECK(ctx);
+        const int64_t rows = static_cast<int64_t>(o->P_local) * A;
+        fill_kernel<<<grid_for(rows, 256), 256, 0, st>>>(o->d_pbr, -INFINITY, rows); BB_LAUNCH_CHECK(ctx);
+      }
+      fill_kernel<<<1, 256, 0, st>>>(o->d_gbr, -INFINITY, A); BB_LAUNCH_CHECK(ctx);
+      break;
+    }
+    default: break;  // CEM: no warm start (cem.py:133-134); RandomSearch: stateless
+  }
+  float* act_out = action ? action : o->d_action;
+  float* next_out = next_state ? next_state : o->d_next;
+  float* rew_out = reward ? reward : o->d_reward;
+  first_action_kernel<<<grid_for(A * dU, 128), 128, 0, st>>>(sol, act_out, o->d_lb, o->d_ub, A, H, dU, sol_stride, add_noise,
+                                                            ctx->seed, o->act_call);
+  BB_LAUNCH_CHECK(ctx);
+  // predict_next_state + evaluate_next_reward on the A executed actions (optimizer_base.py:91-94)
+  StepIO io{o->d_state, act_out, nullptr, next_out, rew_out, nullptr, A, 3};
+  if (int rc = launch_step_simt(ctx, io, st)) return rc;
+  o->act_call++;
+  o->began = false;
+  (void)dS;
+  return BBMPC_OK;
+}
+
+int bbmpc_opt_call(bbmpc_opt* o, const float* state, int time_step, int add_noise, float* action, float* next_state,
+                   float* reward, void* stream) {
+  if (!o) return BBMPC_EINVAL;
+  if (o->world != 1) return opt_fail(o, BBMPC_ESTATE, "bbmpc_opt_call on a sharded optimizer: use begin/iter_local/iter_merge/finish");
+  if (int rc = bbmpc_opt_begin(o, state, time_step, stream)) return rc;
+  const int n = bbmpc_opt_num_iterations(o);
+  for (int it = 0; it < n; ++it) {
+    if (int rc = bbmpc_opt_iter_local(o, it, nullptr, stream)) return rc;
+    if (int rc = bbmpc_opt_iter_merge(o, it, nullptr, 1, stream)) return rc;
+  }
+  return bbmpc_opt_finish(o, add_noise, action, next_state, reward, stream);
+}
+
+int bbmpc_opt_call_host(bbmpc_opt* o, const float* state_host, int time_step, int add_noise, float* action_host,
+                        float* next_state_host, float* reward_host, void* stream) {
+  if (!o) return BBMPC_EINVAL;
+  bbmpc_ctx* ctx = o->ctx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!state_host || !action_host) return opt_fail(o, BBMPC_EINVAL, "NULL host buffer");
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int A = o->cfg.num_agents, dS = o->cfg.dS, dU = o->cfg.dU;
+  float* h_state = o->h_pinned; float* h_action = h_state + A * dS; float* h_next = h_action + A * dU; float* h_rew = h_next + A * dS;
+  std::memcpy(h_state, state_host, A * dS * sizeof(float));
+  BB_CUDA(ctx, cudaMemcpyAsync(o->d_state, h_state, A * dS * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (int rc = bbmpc_opt_call(o, o->d_state, time_step, add_noise, o->d_action, o->d_next, o->d_reward, stream)) return rc;
+  BB_CUDA(ctx, cudaMemcpyAsync(h_action, o->d_action, A * dU * sizeof(float), cudaMemcpyDeviceToHost, st));
+  BB_CUDA(ctx, cudaMemcpyAsync(h_next, o->d_next, A * dS * sizeof(float), cudaMemcpyDeviceToHost, st));
+  BB_CUDA(ctx, cudaMemcpyAsync(h_rew, o->d_reward, A * sizeof(float), cudaMemcpyDeviceToHost, st));
+  BB_CUDA(ctx, cudaStreamSynchronize(st));
+  std::memcpy(action_host, h_action, A * dU * sizeof(float));
+  if (next_state_host) std::memcpy(next_state_host, h_next, A * dS * sizeof(float));
+  if (reward_host) std::memcpy(reward_host, h_rew, A * sizeof(float));
+  return BBMPC_OK;
+}
+
+int64_t bbmpc_opt_get_tensor(bbmpc_opt* o, const char* name, float* out, int64_t n_floats, void* stream) {
+  if (!o || !name) return BBMPC_EINVAL;
+  bbmpc_ctx* ctx = o->ctx;
+  const int A = o->cfg.num_agents;
+  const int64_t rows = static_cast<int64_t>(o->n_eval) * A, pop = static_cast<int64_t>(o->P_local) * A;
+  const float* src = nullptr; int64_t n = 0;
+  const std::string s(name);
+  if (s == "mean" || s == "solution") { src = o->d_mean; n = o->AHU; }
+  else if (s == "variance") { src = o->d_var; n = o->AHU; }
+  else if (s == "previous_solution" || s == "current_parameters") { src = o->d_prev; n = o->AHU; }
+  else if (s == "samples" || s == "x") { src = o->d_samples; n = rows * o->HU; }
+  else if (s == "returns") { src = o->d_returns; n = rows; }
+  else if (s == "partial") { src = o->d_partial; n = partial_floats(o); }
+  else if (s == "v") { src = o->d_v; n = pop * o->HU; }
+  else if (s == "pbest_x") { src = o->d_pbx; n = pop * o->HU; }
+  else if (s == "pbest_r") { src = o->d_pbr; n = pop; }
+  else if (s == "gbest_x") { src = o->d_gbx; n = o->AHU; }
+  else if (s == "gbest_r") { src = o->d_gbr; n = A; }
+  if (!src) return fail(ctx, BBMPC_EINVAL, "unknown or unavailable tensor '%s'", name);
+  if (out && n_floats > 0) {
+    const int64_t m = n_floats < n ? n_floats : n;
+    cudaError_t e = cudaMemcpyAsync(out, src, m * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(ctx, BBMPC_ECUDA, "get_tensor copy: %s", cudaGetErrorString(e));
+  }
+  return n;
+}
+
+int bbmpc_opt_set_sample_trace(bbmpc_opt* o, float* trace, int64_t n_floats) {
+  if (!o) return BBMPC_EINVAL;
+  o->trace = trace; o->trace_floats = trace ? n_floats : 0;
+  return BBMPC_OK;
+}
+
+}  // extern "C"

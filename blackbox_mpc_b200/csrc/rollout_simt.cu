@@ -1,0 +1,270 @@
+// rollout_simt.cu — fp32 CUDA-core path of the trajectory evaluator.
+//
+// Parity-grade restatement of trajectory_evaluators/deterministic.py:48-77 fused into one kernel:
+// process_input -> dynamics_function -> process_output -> reward, H times, state on chip.
+// Serves (a) BBMPC_PREC_FP32, (b) models the tensor-core path cannot hold (wide layers),
+// (c) analytical dynamics (pendulum), (d) the A-row tail of OptimizerBase.__call__
+// (optimizers/optimizer_base.py:91-94) and the stand-alone predict/reward/forward entry points.
+//
+// Layout: a CTA owns TR=32 trajectories (lane = trajectory), its 4 warps split the output
+// features of each layer in blocks of 16.  Activations live in shared memory as [feature][row]
+// (conflict-free for lane = row); weights are read through the read-only path with warp-uniform
+// 128-bit loads from the zero-padded fp32 image W32[K][ldw].
+#include "common.cuh"
+#include "device_fns.cuh"
+
+namespace bbmpc {
+
+constexpr int TR = 32;   // trajectories per CTA
+constexpr int NG = 4;    // warps = feature groups
+constexpr int FT = 16;   // features per thread per pass
+
+struct SimtParams {
+  MlpDev mlp;
+  NormDev norm;
+  int dyn_id, reward_id, dS, dU;
+  // rollout
+  const float* states; const float* actions; float* returns; const float* penalty;
+  int rows, A, H;
+  // single step
+  StepIO io;
+};
+
+struct SimtSmem {
+  float *X, *bufA, *bufB, *S, *S2, *Y, *Act;
+};
+
+__device__ inline SimtSmem carve(float* base, int dS, int dU, int maxw) {
+  SimtSmem s;
+  s.X = base;                base += (dS + dU) * TR;
+  s.bufA = base;             base += maxw * TR;
+  s.bufB = base;             base += maxw * TR;
+  s.S = base;                base += dS * TR;
+  s.S2 = base;               base += dS * TR;
+  s.Y = base;                base += dS * TR;
+  s.Act = base;
+  return s;
+}
+static size_t simt_smem_bytes(int dS, int dU, int maxw) {
+  return static_cast<size_t>((dS + dU) + 2 * maxw + 3 * dS + dU) * TR * sizeof(float);
+}
+
+// One Dense layer for the CTA's 32 rows: out[f][lane] = act(sum_k in[k][lane] * W[k][f] + b[f]).
+// When `accum` is set the (linear or activated) result is added to out instead (ensemble sum).
+__device__ inline void dense_layer(const float* __restrict__ in, float* __restrict__ out,
+                                   const float* __restrict__ W, const float* __restrict__ b, int K, int N,
+                                   int ldw, int act, bool accum, int lane, int g) {
+  for (int f0 = g * FT; f0 < ldw; f0 += NG * FT) {
+    float acc[FT];
+#pragma unroll
+    for (int j = 0; j < FT; ++j) acc[j] = 0.0f;
+    const float* wp = W + f0;
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+      const float a = in[k * TR + lane];
+      const float4* w4 = reinterpret_cast<const float4*>(wp + static_cast<size_t>(k) * ldw);
+#pragma unroll
+      for (int q = 0; q < FT / 4; ++q) {
+        const float4 w = __ldg(w4 + q);
+        acc[4 * q + 0] = fmaf(a, w.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(a, w.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(a, w.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(a, w.w, acc[4 * q + 3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < FT; ++j) {
+      const int f = f0 + j;
+      if (f < N) {
+        const float v = act_exact(__fadd_rn(acc[j], __ldg(b + f)), act);
+        float* o = out + f * TR + lane;
+        *o = accum ? __fadd_rn(*o, v) : v;
+      }
+    }
+  }
+}
+
+// Raw dynamics_function(x): X[dS+dU][TR] -> Y[dS][TR]  (ensemble: member-order sum, then / n).
+template <int DYN>
+__device__ inline void dynamics_raw(const SimtParams& p, const SimtSmem& sm, int lane, int g) {
+  if (DYN == BBMPC_DYN_MLP) {
+    const MlpDev& m = p.mlp;
+    for (int mm = 0; mm < m.n_members; ++mm) {
+      const float* in = sm.X;
+      for (int l = 0; l < m.n_layers; ++l) {
+        const LayerDev& L = m.layer[l];
+        const bool last = (l == m.n_layers - 1);
+        float* out = last ? sm.Y : ((l & 1) ? sm.bufB : sm.bufA);
+        const float* W = m.w32 + L.w_off + mm * m.w_member_stride;
+        const float* b = m.w32 + L.b_off + mm * m.w_member_stride;
+        dense_layer(in, out, W, b, L.K, L.N, L.ldw, L.act, last && mm > 0, lane, g);
+        __syncthreads();
+        in = out;
+      }
+    }
+    if (m.n_members > 1) {
+      const float n = static_cast<float>(m.n_members);
+      for (int i = g; i < p.dS; i += NG) sm.Y[i * TR + lane] = __fdiv_rn(sm.Y[i * TR + lane], n);
+      __syncthreads();
+    }
+  } else {  // pendulum: X = [cos, sin, thdot, u]
+    if (g == 0) {
+      float s[3], a[1], dev[3];
+      s[0] = sm.X[0 * TR + lane]; s[1] = sm.X[1 * TR + lane]; s[2] = sm.X[2 * TR + lane];
+      a[0] = sm.X[3 * TR + lane];
+      pendulum_deviation(s, a, dev);
+      sm.Y[0 * TR + lane] = dev[0]; sm.Y[1 * TR + lane] = dev[1]; sm.Y[2 * TR + lane] = dev[2];
+    }
+    __syncthreads();
+  }
+}
+
+// process_input (system_dynamics_handler.py:97-126): S, Act -> X.
+__device__ inline void build_input(const SimtParams& p, const SimtSmem& sm, int lane, int g, bool norm_on) {
+  for (int k = g; k < p.dS + p.dU; k += NG) {
+    float v;
+    if (k < p.dS) {
+      v = sm.S[k * TR + lane];
+      if (norm_on) v = __fdiv_rn(__fsub_rn(v, p.norm.mean_s[k]), p.norm.den_s[k]);
+    } else {
+      v = sm.Act[(k - p.dS) * TR + lane];
+      if (norm_on) v = __fdiv_rn(__fsub_rn(v, p.norm.mean_a[k - p.dS]), p.norm.den_a[k - p.dS]);
+    }
+    sm.X[k * TR + lane] = v;
+  }
+}
+// process_output (system_dynamics_handler.py:128-161) + utils/transforms.py:34: Y, S -> S2.
+__device__ inline void build_output(const SimtParams& p, const SimtSmem& sm, int lane, int g, bool norm_on) {
+  for (int i = g; i < p.dS; i += NG) {
+    float d = sm.Y[i * TR + lane];
+    if (norm_on) d = __fadd_rn(p.norm.mean_t[i], __fmul_rn(d, p.norm.den_t[i]));
+    sm.S2[i * TR + lane] = __fadd_rn(d, sm.S[i * TR + lane]);
+  }
+}
+
+__device__ inline float row_reward(const SimtParams& p, const SimtSmem& sm, int lane) {
+  float s[MAX_DS], s2[MAX_DS], a[MAX_DU];
+  for (int i = 0; i < p.dS; ++i) { s[i] = sm.S[i * TR + lane]; s2[i] = sm.S2[i * TR + lane]; }
+  for (int i = 0; i < p.dU; ++i) a[i] = sm.Act[i * TR + lane];
+  return reward_dispatch(p.reward_id, s, a, s2, p.dS, p.dU);
+}
+
+template <int DYN>
+__global__ void __launch_bounds__(TR* NG) rollout_simt_kernel(const SimtParams p) {
+  extern __shared__ float smem_f[];
+  const SimtSmem sm = carve(smem_f, p.dS, p.dU, DYN == BBMPC_DYN_MLP ? p.mlp.max_width : 4);
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int row = blockIdx.x * TR + lane;
+  const bool valid = row < p.rows;
+  const int arow = valid ? row : 0;
+  const bool norm_on = (DYN == BBMPC_DYN_MLP) && p.norm.enabled;
+
+  for (int i = g; i < p.dS; i += NG) sm.S[i * TR + lane] = p.states[(arow % p.A) * p.dS + i];
+  float ret = 0.0f;
+  for (int t = 0; t < p.H; ++t) {
+    for (int i = g; i < p.dU; i += NG)
+      sm.Act[i * TR + lane] = p.actions[(static_cast<size_t>(arow) * p.H + t) * p.dU + i];
+    __syncthreads();
+    build_input(p, sm, lane, g, norm_on);
+    __syncthreads();
+    dynamics_raw<DYN>(p, sm, lane, g);
+    build_output(p, sm, lane, g, norm_on);
+    __syncthreads();
+    if (g == 0) ret = __fadd_rn(ret, row_reward(p, sm, lane));
+    __syncthreads();
+    for (int i = g; i < p.dS; i += NG) sm.S[i * TR + lane] = sm.S2[i * TR + lane];
+  }
+  if (g == 0 && valid) {
+    float r = isnan(ret) ? -1e6f : ret;  // deterministic.py:75-77 (NaN only, not +-inf)
+    if (p.penalty) r = __fsub_rn(r, p.penalty[row]);
+    p.returns[row] = r;
+  }
+}
+
+template <int DYN>
+__global__ void __launch_bounds__(TR* NG) step_simt_kernel(const SimtParams p) {
+  extern __shared__ float smem_f[];
+  const SimtSmem sm = carve(smem_f, p.dS, p.dU, DYN == BBMPC_DYN_MLP ? p.mlp.max_width : 4);
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int row = blockIdx.x * TR + lane;
+  const bool valid = row < p.io.B;
+  const int arow = valid ? row : 0;
+  const bool norm_on = (DYN == BBMPC_DYN_MLP) && p.norm.enabled;
+  const int mode = p.io.mode;
+
+  if (mode & 4) {  // raw dynamics_function(x)
+    for (int k = g; k < p.dS + p.dU; k += NG) sm.X[k * TR + lane] = p.io.s[static_cast<size_t>(arow) * (p.dS + p.dU) + k];
+    __syncthreads();
+    dynamics_raw<DYN>(p, sm, lane, g);
+    if (valid) for (int i = g; i < p.dS; i += NG) p.io.raw_out[static_cast<size_t>(row) * p.dS + i] = sm.Y[i * TR + lane];
+    return;
+  }
+  for (int i = g; i < p.dS; i += NG) sm.S[i * TR + lane] = p.io.s[static_cast<size_t>(arow) * p.dS + i];
+  for (int i = g; i < p.dU; i += NG) sm.Act[i * TR + lane] = p.io.a[static_cast<size_t>(arow) * p.dU + i];
+  __syncthreads();
+  if (mode & 1) {
+    build_input(p, sm, lane, g, norm_on);
+    __syncthreads();
+    dynamics_raw<DYN>(p, sm, lane, g);
+    build_output(p, sm, lane, g, norm_on);
+    __syncthreads();
+    if (valid && p.io.s2_out)
+      for (int i = g; i < p.dS; i += NG) p.io.s2_out[static_cast<size_t>(row) * p.dS + i] = sm.S2[i * TR + lane];
+  } else {
+    for (int i = g; i < p.dS; i += NG) sm.S2[i * TR + lane] = p.io.s2_in[static_cast<size_t>(arow) * p.dS + i];
+    __syncthreads();
+  }
+  if ((mode & 2) && g == 0 && valid) p.io.reward_out[row] = row_reward(p, sm, lane);
+}
+
+static int fill_params(bbmpc_ctx* ctx, SimtParams& p) {
+  const ModelHost& m = ctx->model;
+  p.mlp = m.mlp; p.norm = m.norm; p.dyn_id = m.dyn_id; p.reward_id = ctx->reward_id; p.dS = m.dS; p.dU = m.dU;
+  if (m.dyn_id == BBMPC_DYN_MLP && m.mlp.max_width > 800)
+    return fail(ctx, BBMPC_EINVAL, "fp32 path supports layer widths up to 800 (got %d)", m.mlp.max_width);
+  return BBMPC_OK;
+}
+
+template <typename K>
+static int set_smem(bbmpc_ctx* ctx, K kernel, size_t bytes) {
+  BB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  return BBMPC_OK;
+}
+
+int launch_rollout_simt(bbmpc_ctx* ctx, const float* states, const float* actions, float* returns,
+                        const float* penalty, int rows, int A, int H, int, cudaStream_t st) {
+  SimtParams p{};
+  if (int rc = fill_params(ctx, p)) return rc;
+  p.states = states; p.actions = actions; p.returns = returns; p.penalty = penalty;
+  p.rows = rows; p.A = A; p.H = H;
+  const int grid = (rows + TR - 1) / TR;
+  if (p.dyn_id == BBMPC_DYN_MLP) {
+    const size_t sb = simt_smem_bytes(p.dS, p.dU, p.mlp.max_width);
+    if (int rc = set_smem(ctx, rollout_simt_kernel<BBMPC_DYN_MLP>, sb)) return rc;
+    rollout_simt_kernel<BBMPC_DYN_MLP><<<grid, TR * NG, sb, st>>>(p);
+  } else {
+    const size_t sb = simt_smem_bytes(p.dS, p.dU, 4);
+    rollout_simt_kernel<BBMPC_DYN_PENDULUM><<<grid, TR * NG, sb, st>>>(p);
+  }
+  BB_LAUNCH_CHECK(ctx);
+  return BBMPC_OK;
+}
+
+int launch_step_simt(bbmpc_ctx* ctx, const StepIO& io, cudaStream_t st) {
+  SimtParams p{};
+  if (int rc = fill_params(ctx, p)) return rc;
+  p.io = io;
+  const int grid = (io.B + TR - 1) / TR;
+  if (p.dyn_id == BBMPC_DYN_MLP && ctx->model.set) {
+    const size_t sb = simt_smem_bytes(p.dS, p.dU, p.mlp.max_width);
+    if (int rc = set_smem(ctx, step_simt_kernel<BBMPC_DYN_MLP>, sb)) return rc;
+    step_simt_kernel<BBMPC_DYN_MLP><<<grid, TR * NG, sb, st>>>(p);
+  } else {
+    const size_t sb = simt_smem_bytes(p.dS, p.dU, 4);
+    step_simt_kernel<BBMPC_DYN_PENDULUM><<<grid, TR * NG, sb, st>>>(p);
+  }
+  BB_LAUNCH_CHECK(ctx);
+  return BBMPC_OK;
+}
+
+}  // namespace bbmpc

@@ -1,0 +1,116 @@
+"""SystemDynamicsHandler — inference half.
+
+Mirrors blackbox_mpc/dynamics_handlers/system_dynamics_handler.py:7-161: constructor signature,
+process_input (:97-126), process_output (:128-161), normalisation statistics (six fp32 vectors,
+:84-95, :340-348).  The handler owns the Engine (one bbmpc_ctx = this model on this GPU) and
+re-stages weights/statistics into libbbmpc whenever the dynamics function's version changes (the
+handler is shared with the trainer in the reference, utils/iterative_mpc.py:147-157).
+
+The training half (train / _training_algorithm / save, :163-349) is out of scope (SURVEY §2 #3')."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..engine import Engine
+
+_STAT_NAMES = ("mean_states", "std_states", "mean_actions", "std_actions", "mean_targets", "std_targets")
+
+
+def stage_model(engine: Engine, dynamics_function) -> None:
+    """bbmpc_model_set_mlp / bbmpc_model_set_builtin for a dynamics_function object."""
+    lib = engine.lib
+    builtin = getattr(dynamics_function, "bbmpc_dynamics_id", None)
+    if builtin is not None:
+        engine.check(lib.bbmpc_model_set_builtin(engine.handle, builtin, dynamics_function.dim_S, dynamics_function.dim_U))
+        return
+    if not hasattr(dynamics_function, "members"):
+        raise TypeError(
+            "dynamics_function must be a DeterministicMLP / EnsembleMLP or a built-in analytical model "
+            "(e.g. utils.pendulum.PendulumTrueModel): arbitrary Python callables cannot be fused into "
+            "the sm_100a rollout kernel")
+    members = dynamics_function.members()
+    dims = dynamics_function.layer_sizes
+    n_layers = len(dims) - 1
+    n = len(members) * n_layers
+    W = (C.c_void_p * n)(*[m.weights[l].data_ptr() for m in members for l in range(n_layers)])
+    B = (C.c_void_p * n)(*[m.biases[l].data_ptr() for m in members for l in range(n_layers)])
+    for m in members:
+        for t in m.weights + m.biases:
+            assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32
+    engine.check(lib.bbmpc_model_set_mlp(engine.handle, len(members), n_layers, (C.c_int * (n_layers + 1))(*dims), W, B,
+                                         (C.c_int * n_layers)(*dynamics_function.activation_ids), engine.stream()))
+
+
+class SystemDynamicsHandler:
+    def __init__(self, env_action_space, env_observation_space, dynamics_function=None, true_model=False,
+                 is_normalized=True, log_dir=None, tf_writer=None, save_model_frequency=1, saved_model_dir=None,
+                 transform_targets_func=None, inverse_transform_targets_func=None,
+                 device: Optional[int] = None, seed: int = 0, precision: str = "auto"):
+        if transform_targets_func is not None or inverse_transform_targets_func is not None:
+            raise NotImplementedError("only the default target transform (next - current) is fused")
+        self._is_true_model = bool(true_model)
+        self._dim_S = int(env_observation_space.shape[0])
+        self._dim_U = int(env_action_space.shape[0])
+        self._dynamics_function = dynamics_function
+        self._is_normalized = bool(is_normalized)
+        self._log_dir, self._tf_writer = log_dir, tf_writer
+        self._save_model_frequency, self._saved_model_dir = save_model_frequency, saved_model_dir
+        self.engine = Engine(device=device, seed=seed, precision=precision)
+        self._stats = None          # six CUDA tensors once set
+        self._stats_version = 0
+        self._staged = (None, -1, -1)   # (id(dynamics_function), its version, stats version)
+        if saved_model_dir is not None and self._is_normalized and not self._is_true_model:
+            # same six file names as the reference (:84-95)
+            self.set_normalization(*[np.load(os.path.join(saved_model_dir, n + ".npy")) for n in _STAT_NAMES])
+
+    # -- statistics ---------------------------------------------------------------------------
+    def set_normalization(self, mean_states, std_states, mean_actions, std_actions, mean_targets, std_targets):
+        dev = self.engine.device
+        vals = [torch.as_tensor(np.asarray(v), dtype=torch.float32).to(dev).contiguous()
+                for v in (mean_states, std_states, mean_actions, std_actions, mean_targets, std_targets)]
+        for v, n in zip(vals, (self._dim_S, self._dim_S, self._dim_U, self._dim_U, self._dim_S, self._dim_S)):
+            if v.numel() != n:
+                raise ValueError("normalisation statistic of the wrong length")
+        (self._mean_states, self._std_states, self._mean_actions, self._std_actions,
+         self._mean_targets, self._std_targets) = vals
+        self._stats = vals
+        self._stats_version += 1
+
+    # -- staging ------------------------------------------------------------------------------
+    def ensure_staged(self) -> Engine:
+        f = self._dynamics_function
+        if f is None:
+            raise RuntimeError("SystemDynamicsHandler has no dynamics_function")
+        key = (id(f), getattr(f, "version", 0), self._stats_version)
+        if key != self._staged:
+            e, lib = self.engine, self.engine.lib
+            use_norm = self._is_normalized and not self._is_true_model
+            if use_norm and self._stats is None:
+                raise RuntimeError("is_normalized=True but no statistics were set "
+                                   "(set_normalization(...) or saved_model_dir)")
+            p = [_lib.ptr(t) for t in self._stats] if use_norm else [None] * 6
+            e.check(lib.bbmpc_model_set_norm(e.handle, self._dim_S, self._dim_U, p[0], p[1], p[2], p[3], p[4], p[5], e.stream()))
+            stage_model(e, f)
+            self._staged = key
+        return self.engine
+
+    # -- reference-API tensor functions (used outside the fused path, e.g. by user code) -------
+    def process_input(self, states, actions):
+        if self._is_true_model or not self._is_normalized:
+            return torch.cat([states, actions], dim=-1)
+        return torch.cat([(states - self._mean_states) / (self._std_states + 1e-7),
+                          (actions - self._mean_actions) / (self._std_actions + 1e-7)], dim=-1)
+
+    def process_output(self, inputs_states, raw_output):
+        if self._is_true_model or not self._is_normalized:
+            return raw_output + inputs_states
+        return (self._mean_targets + raw_output * (self._std_targets + 1e-7)) + inputs_states
+
+    def train(self, *args, **kwargs):
+        raise NotImplementedError("dynamics training is outside the B200 hot path (SURVEY §8f-2)")

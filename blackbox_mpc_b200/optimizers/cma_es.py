@@ -1,0 +1,19 @@
+"""CMAESOptimizer (blackbox_mpc/optimizers/cma_es.py:6-227) — constructor surface only in this
+round; the covariance refit kernels are the next row of SURVEY §8 (a16)."""
+from .. import _lib
+from .optimizer_base import OptimizerBase
+
+
+class CMAESOptimizer(OptimizerBase):
+    KIND = _lib.OPT_CMAES
+
+    def __init__(self, env_action_space, env_observation_space, planning_horizon=50, max_iterations=5,
+                 population_size=500, num_elite=50, h_sigma=1.0, alpha_cov=2.0, num_agents=5):
+        super().__init__(name=None, planning_horizon=planning_horizon, max_iterations=max_iterations,
+                         num_agents=num_agents, env_action_space=env_action_space,
+                         env_observation_space=env_observation_space)
+        self._population_size, self._num_elite = int(population_size), int(num_elite)
+        self._h_sigma, self._alpha_cov = float(h_sigma), float(alpha_cov)
+
+    def _config(self):
+        return dict(num_elite=self._num_elite, h_sigma=self._h_sigma, alpha_cov=self._alpha_cov)

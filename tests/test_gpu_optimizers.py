@@ -1,0 +1,153 @@
+"""GPU parity of the optimizer loop: the CUDA path's own draws are recorded (sample trace) and
+injected into the oracle, so sampling->rollout->refit is compared on identical inputs."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import oracle
+from blackbox_mpc_b200.utils import workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_with_trace(w, name, precision="fp32"):
+    policy = workloads.build_policy(w, precision=precision, optimizer_name=name)
+    opt = policy._optimizer
+    trace = opt.enable_sample_trace()
+    state = torch.from_numpy(w.state)
+    action, nxt, rew = opt(state, 0, False)
+    torch.cuda.synchronize()
+    shape = (-1, w.num_agents, w.planning_horizon, w.dU)
+    return policy, opt, [t.reshape(shape).cpu() for t in trace], action.cpu(), nxt.cpu(), rew.cpu()
+
+
+@pytest.mark.parametrize("name,P,A", [("C2", 400, 1), ("C2", 300, 3), ("C4", 256, 1)])
+def test_cem_matches_oracle(cuda_device, name, P, A):
+    w = workloads.make(name, population_size=P, num_agents=A, bias_scale=0.1)
+    w.optimizer_args = dict(num_elite=20, alpha=0.25)
+    policy, opt, samples, action, nxt, rew = _run_with_trace(w, "CEM")
+    o = helpers.oracle_optimizer(w, "CEM", dtype=torch.float64)
+    draws = oracle.InjectedDraws({"cem.samples": samples}, dtype=torch.float64)
+    ref_action, ref_next, ref_rew = o(torch.from_numpy(w.state).double(), 0, False, draws)
+    # elite sets may differ only where returns tie within fp32 noise; compare the refit statistics
+    np.testing.assert_allclose(opt.get_tensor("mean").cpu().numpy().reshape(A, -1),
+                               o.trace[-1]["mean"].reshape(A, -1).numpy(), rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(opt.get_tensor("variance").cpu().numpy().reshape(A, -1),
+                               o.trace[-1]["variance"].reshape(A, -1).numpy(), rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(action.numpy(), ref_action.numpy(), rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(nxt.numpy(), ref_next.numpy(), rtol=1e-4, atol=2e-4)
+    # samples honour the +-2 sigma truncation and the constrained variance: always inside the box
+    for s in samples:
+        assert (s >= torch.from_numpy(w.lb) - 1e-6).all() and (s <= torch.from_numpy(w.ub) + 1e-6).all()
+
+
+@pytest.mark.parametrize("opt_name", ["PI2", "RandomSearch", "SPSA"])
+def test_other_optimizers_match_oracle(cuda_device, opt_name):
+    w = workloads.make("C2", population_size=300, num_agents=2, bias_scale=0.1)
+    policy, opt, samples, action, nxt, rew = _run_with_trace(w, opt_name)
+    o = helpers.oracle_optimizer(w, opt_name, dtype=torch.float64)
+    st = torch.from_numpy(w.state).double()
+    if opt_name == "SPSA":
+        # the trace holds [plus; minus] clipped parameters; recover delta = sign(plus - minus)
+        P = w.population_size
+        mids = []
+        deltas = []
+        for s in samples:
+            plus, minus = s[:P], s[P:]
+            deltas.append(torch.sign(plus - minus))
+        assert all((d.abs() == 1).all() for d in deltas)
+        draws = oracle.InjectedDraws({"spsa.delta": deltas}, dtype=torch.float64)
+    else:
+        tag = {"PI2": "pi2.samples", "RandomSearch": "rs.samples"}[opt_name]
+        draws = oracle.InjectedDraws({tag: samples}, dtype=torch.float64)
+    ref_action, ref_next, ref_rew = o(st, 0, False, draws)
+    np.testing.assert_allclose(action.numpy(), ref_action.numpy(), rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(nxt.numpy(), ref_next.numpy(), rtol=2e-4, atol=2e-4)
+    # second act(): warm start state (PI2/SPSA shift) must match too
+    if opt_name in ("PI2", "SPSA"):
+        key = "previous_solution"
+        ref_prev = o._previous_solution if opt_name == "PI2" else o._current_parameters
+        np.testing.assert_allclose(opt.get_tensor(key).cpu().numpy().reshape(ref_prev.shape), ref_prev.numpy(), rtol=2e-4, atol=2e-4)
+
+
+def test_pso_matches_oracle(cuda_device):
+    w = workloads.make("C2", population_size=200, num_agents=2, bias_scale=0.1)
+    policy = workloads.build_policy(w, precision="fp32", optimizer_name="PSO")
+    opt = policy._optimizer
+    opt.reset()
+    x0 = opt.get_tensor("x").cpu().reshape(200, 2, w.planning_horizon, w.dU)
+    v0 = opt.get_tensor("v").cpu().reshape_as(x0)
+    lb, ub = torch.from_numpy(w.lb), torch.from_numpy(w.ub)
+    assert (x0 >= lb).all() and (x0 <= ub).all() and (v0.abs() <= 0.01 * (ub - lb) + 1e-7).all()
+    action, nxt, rew = opt(torch.from_numpy(w.state), 0, False)
+    torch.cuda.synchronize()
+    # oracle with the same initial swarm; r1/r2 and the re-seed draws cannot be injected from the
+    # outside, so compare the first iteration's personal/global best bookkeeping instead
+    o = helpers.oracle_optimizer(w, "PSO", dtype=torch.float64, max_iterations=1)
+    o._x, o._v, o._pbest_x = x0.double(), v0.double(), x0.double()
+    o._pbest_r = torch.full((200, 2), -float("inf"), dtype=torch.float64)
+
+    class D(oracle.TorchDraws):
+        pass
+    o(torch.from_numpy(w.state).double(), 0, False, D(0, torch.float64))
+    # after one oracle iteration gbest == argmax of plain rollout returns of x0
+    ev = policy._trajectory_evaluator
+    r0 = ev(torch.from_numpy(w.state), x0, 0).cpu()
+    best = r0.argmax(dim=0)
+    for a in range(2):
+        np.testing.assert_allclose(o.trace[0]["gbest_x"][a].numpy(), x0[best[a], a].numpy(), rtol=0, atol=1e-6)
+    assert torch.isfinite(action).all() and (action >= lb).all() and (action <= ub).all()
+
+
+def test_mpc_policy_act_marshalling(cuda_device):
+    """policies/mpc_policy.py:149-172: 1-D obs -> tiled to A rows -> un-batched outputs."""
+    w = workloads.make("C2", population_size=200, num_agents=3, bias_scale=0.1)
+    policy = workloads.build_policy(w)
+    a, n, r = policy.act(w.state[0], 0)
+    assert a.shape == (w.dU,) and n.shape == (w.dS,) and np.ndim(r) == 0
+    a2, n2, r2 = policy.act(w.state, 1)
+    assert a2.shape == (3, w.dU) and n2.shape == (3, w.dS) and r2.shape == (3,)
+    assert (a2 >= w.lb).all() and (a2 <= w.ub).all()
+    policy.reset()
+    a3, _, _ = policy.act(w.state, 2, exploration_noise=True)
+    assert (a3 >= w.lb).all() and (a3 <= w.ub).all()
+    policy.switch_optimizer(optimizer_name="RandomSearch", planning_horizon=10, population_size=128)
+    a4, _, _ = policy.act(w.state, 3)
+    assert a4.shape == (3, w.dU)
+
+
+def test_shard_invariance_single_gpu(cuda_device):
+    """Sharded (2 and 3 ranks emulated on one GPU through begin/iter_local/iter_merge/finish) equals
+    unsharded: samples are keyed on the global row, merge is exact."""
+    import ctypes as C
+    from blackbox_mpc_b200 import _lib
+    w = workloads.make("C2", population_size=301, num_agents=2, bias_scale=0.1)
+    w.optimizer_args = dict(num_elite=16, alpha=0.25)
+    ref_policy = workloads.build_policy(w, precision="fp32")
+    ref_action, _, _ = ref_policy._optimizer(torch.from_numpy(w.state), 0, False)
+    ref_mean = ref_policy._optimizer.get_tensor("mean").cpu()
+    for world in (2, 3):
+        pols = [workloads.build_policy(w, precision="fp32") for _ in range(world)]
+        opts = [p._optimizer for p in pols]
+        for r, o in enumerate(opts):
+            o.shard(r, world)
+            o._ensure_handle()
+        lib = opts[0]._engine.lib
+        dev = opts[0]._engine.device
+        n = lib.bbmpc_opt_partial_floats(opts[0]._handle)
+        gathered = torch.empty(world, n, device=dev)
+        state = torch.from_numpy(w.state).to(dev)
+        for o in opts:
+            o._engine.check(lib.bbmpc_opt_begin(o._handle, _lib.ptr(state), 0, None))
+        for it in range(lib.bbmpc_opt_num_iterations(opts[0]._handle)):
+            for r, o in enumerate(opts):
+                o._engine.check(lib.bbmpc_opt_iter_local(o._handle, it, gathered[r].data_ptr(), None))
+            for o in opts:
+                o._engine.check(lib.bbmpc_opt_iter_merge(o._handle, it, _lib.ptr(gathered), world, None))
+        for o in opts:
+            act = torch.empty(2, w.dU, device=dev)
+            o._engine.check(lib.bbmpc_opt_finish(o._handle, 0, _lib.ptr(act), None, None, None))
+            torch.cuda.synchronize()
+            assert torch.equal(o.get_tensor("mean").cpu(), ref_mean), f"world={world}"
+            assert torch.equal(act.cpu(), ref_action.cpu())

@@ -1,0 +1,108 @@
+"""GPU parity: bbmpc_rollout / predict_next_state / reward (through the Python plugin classes, i.e.
+through the C ABI) against the oracle on identical seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from blackbox_mpc_b200.utils import workloads
+
+pytestmark = pytest.mark.gpu
+
+# fp32 path: same arithmetic as the reference up to summation order.  bf16x3: operands carry 16
+# mantissa bits, products ~2^-17 relative; the recurrence amplifies that over H steps.
+TOL = {"fp32": dict(atol=2e-3, rtol=2e-5), "bf16x3": dict(atol=2e-2, rtol=2e-4)}
+STEP_TOL = {"fp32": 2e-5, "bf16x3": 1e-4}
+
+
+def _policy_and_eval(w, precision):
+    policy = workloads.build_policy(w, precision=precision)
+    return policy, policy._trajectory_evaluator
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("name,P,A", [("C2", 300, 1), ("C3", 200, 1), ("C4", 131, 1), ("C4", 64, 3), ("C2", 129, 2)])
+def test_rollout_matches_oracle(cuda_device, name, P, A, precision):
+    w = workloads.make(name, population_size=P, num_agents=A, bias_scale=0.1)
+    _, ev = _policy_and_eval(w, precision)
+    assert ev.engine().effective_precision == precision
+    actions = helpers.random_actions(w, P, seed=1)
+    state = torch.from_numpy(w.state)
+    got = ev(state, actions, 0).cpu().numpy()
+    ref = helpers.oracle_evaluator(w, torch.float64)(state.double(), actions.double(), 0).numpy()
+    assert got.shape == (P, A)
+    helpers.compare_returns(got, ref, max_jump_frac=0.02, **TOL[precision])
+
+
+def test_rollout_pendulum_true_model(cuda_device):
+    w = workloads.make("C1", population_size=500, num_agents=2)
+    _, ev = _policy_and_eval(w, "auto")
+    actions = helpers.random_actions(w, 500, seed=2)
+    state = torch.from_numpy(w.state)
+    got = ev(state, actions, 0).cpu().numpy()
+    ref32 = helpers.oracle_evaluator(w, torch.float32)(state, actions, 0).numpy()
+    ref64 = helpers.oracle_evaluator(w, torch.float64)(state.double(), actions.double(), 0).numpy()
+    np.testing.assert_allclose(got, ref64, rtol=2e-4, atol=2e-3)
+    np.testing.assert_allclose(got, ref32, rtol=2e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C4"])
+def test_single_step_predict_and_reward(cuda_device, name):
+    w = workloads.make(name, num_agents=37, bias_scale=0.1)
+    _, ev = _policy_and_eval(w, "fp32")
+    g = torch.Generator().manual_seed(3)
+    s = torch.from_numpy(w.state)
+    a = torch.from_numpy(w.lb) + torch.from_numpy(w.ub - w.lb) * torch.rand(37, w.dU, generator=g)
+    o = helpers.oracle_evaluator(w, torch.float64)
+    nxt = ev.predict_next_state(s, a).cpu().numpy()
+    ref_nxt = o.predict_next_state(s.double(), a.double()).numpy()
+    np.testing.assert_allclose(nxt, ref_nxt, rtol=2e-5, atol=2e-5)
+    rew = ev.evaluate_next_reward(s, torch.from_numpy(ref_nxt.astype(np.float32)), a).cpu().numpy()
+    ref_rew = o.evaluate_next_reward(s.double(), torch.from_numpy(ref_nxt.astype(np.float32)).double(), a.double()).numpy()
+    helpers.compare_returns(rew, ref_rew, atol=2e-3, rtol=2e-5, max_jump_frac=0.1)
+
+
+def test_dynamics_function_callable(cuda_device):
+    """DeterministicMLP.__call__(x, train) and PendulumTrueModel.__call__ are the reference's
+    dynamics_function plug point (deterministic_mlp.py:27-51, pendulum.py:58-92)."""
+    from blackbox_mpc_b200.dynamics_functions.deterministic_mlp import DeterministicMLP
+    from blackbox_mpc_b200.utils.pendulum import PendulumTrueModel
+    import oracle
+    m = DeterministicMLP([26, 200, 200, 200, 20], ["tanh", "tanh", "tanh", None], seed=5)
+    x = torch.randn(77, 26, generator=torch.Generator().manual_seed(4))
+    got = m(x, False).cpu()
+    ref = oracle.MLP([t.cpu().double() for t in m.weights], [t.cpu().double() for t in m.biases], ["tanh"] * 3 + [None])(x.double())
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
+    xp = torch.randn(50, 4, generator=torch.Generator().manual_seed(6))
+    np.testing.assert_allclose(PendulumTrueModel()(xp, False).cpu().numpy(), oracle.PendulumTrueModel()(xp.double()).numpy(),
+                               rtol=1e-5, atol=1e-5)
+
+
+def test_nan_guard_and_empty(cuda_device):
+    """NaN (not inf) -> -1e6 (deterministic.py:75-77); P = 0 is a no-op."""
+    w = workloads.make("C2", population_size=40, bias_scale=0.1)
+    _, ev = _policy_and_eval(w, "fp32")
+    actions = helpers.random_actions(w, 40, seed=7)
+    actions[3, 0, 5, 0] = float("nan")
+    got = ev(torch.from_numpy(w.state), actions, 0).cpu().numpy()
+    assert got[3, 0] == np.float32(-1e6) and np.isfinite(np.delete(got[:, 0], 3)).all()
+    empty = ev(torch.from_numpy(w.state), actions[:0], 0)
+    assert tuple(empty.shape) == (0, 1)
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE C4 at full size: properties that do not need the oracle — permutation equivariance
+    of the population axis, tile-boundary independence, and fp32 vs bf16x3 agreement."""
+    w = workloads.make("C4", bias_scale=0.1)
+    _, ev3 = _policy_and_eval(w, "bf16x3")
+    actions = helpers.random_actions(w, w.population_size, seed=8)
+    state = torch.from_numpy(w.state)
+    r = ev3(state, actions, 0).cpu()
+    perm = torch.randperm(w.population_size, generator=torch.Generator().manual_seed(9))
+    r_perm = ev3(state, actions[perm], 0).cpu()
+    assert torch.equal(r[perm], r_perm)
+    r_head = ev3(state, actions[:1000], 0).cpu()
+    assert torch.equal(r[:1000], r_head)
+    _, ev32 = _policy_and_eval(w, "fp32")
+    r32 = ev32(state, actions, 0).cpu()
+    helpers.compare_returns(r.numpy(), r32.numpy(), max_jump_frac=0.02, **TOL["bf16x3"])
