@@ -112,6 +112,7 @@ struct SampleArgs {
   float* samples; float* penalty; const float* mean; const float* var; const float* lb; const float* ub;
   int P_local, p0, A, H, dU; uint64_t seed; uint32_t act_call, iter;
   float ck;   // SPSA perturbation size
+  float* raw_trace;  // optional: un-clipped draws of this iteration (PI2), for oracle injection
 };
 
 // cem.py:81-94: cvar = min(((mean-lb)/2)^2, ((ub-mean)/2)^2, var); x = mean + sqrt(cvar)*tn
@@ -153,6 +154,7 @@ __global__ void pi2_sample_kernel(const SampleArgs s, float* raw_excess_sq) {
     const float d = __fsub_rn(x, xf);
     s.samples[pa * HU + e] = xf;
     raw_excess_sq[pa * HU + e] = __fmul_rn(d, d);
+    if (s.raw_trace) s.raw_trace[pa * HU + e] = x;
   }
 }
 // random_search.py:40-41: x = lb + (ub - lb) * U[0,1)
@@ -677,10 +679,12 @@ int bbmpc_opt_iter_local(bbmpc_opt* o, int iter, float* partial_out, void* strea
   const int A = c.num_agents, H = c.planning_horizon, dU = c.dU, HU = o->HU;
   float* partial = partial_out ? partial_out : o->d_partial;
   SampleArgs s{o->d_samples, o->d_penalty, o->d_mean, o->d_var, o->d_lb, o->d_ub, o->P_local, o->p0, A, H, dU,
-               ctx->seed, o->act_call, static_cast<uint32_t>(iter), 0.0f};
+               ctx->seed, o->act_call, static_cast<uint32_t>(iter), 0.0f, nullptr};
   const int64_t rows = static_cast<int64_t>(o->n_eval) * A;
   const int64_t nthr = static_cast<int64_t>(o->P_local) * A * ((HU + 3) / 4);
   const float* penalty = nullptr;
+  const int64_t per_iter = rows * HU;
+  float* trace_slot = (o->trace && (static_cast<int64_t>(iter) + 1) * per_iter <= o->trace_floats) ? o->trace + iter * per_iter : nullptr;
   if (o->P_local > 0) {
     switch (c.kind) {
       case BBMPC_OPT_CEM:
@@ -688,6 +692,7 @@ int bbmpc_opt_iter_local(bbmpc_opt* o, int iter, float* partial_out, void* strea
         break;
       case BBMPC_OPT_PI2:
         s.var = o->d_var0;
+        s.raw_trace = trace_slot;
         pi2_sample_kernel<<<grid_for(nthr, 256), 256, 0, st>>>(s, o->d_work); BB_LAUNCH_CHECK(ctx);
         penalty_kernel<<<grid_for(rows * 32, 256), 256, 0, st>>>(o->d_work, o->d_penalty, rows, HU); BB_LAUNCH_CHECK(ctx);
         penalty = o->d_penalty;
@@ -708,11 +713,8 @@ int bbmpc_opt_iter_local(bbmpc_opt* o, int iter, float* partial_out, void* strea
         break;
       default: return opt_fail(o, BBMPC_EINVAL, "unsupported optimizer kind");
     }
-    if (o->trace) {
-      const int64_t per_iter = rows * HU;
-      if ((static_cast<int64_t>(iter) + 1) * per_iter <= o->trace_floats)
-        BB_CUDA(ctx, cudaMemcpyAsync(o->trace + iter * per_iter, o->d_samples, per_iter * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    }
+    if (trace_slot && c.kind != BBMPC_OPT_PI2)
+      BB_CUDA(ctx, cudaMemcpyAsync(trace_slot, o->d_samples, per_iter * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (int rc = rollout_dispatch(ctx, o->d_state, o->d_samples, o->d_returns, penalty, static_cast<int>(rows), A, H, st)) return rc;
   }
   switch (c.kind) {

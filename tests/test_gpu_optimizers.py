@@ -97,6 +97,7 @@ def test_pso_matches_oracle(cuda_device):
     best = r0.argmax(dim=0)
     for a in range(2):
         np.testing.assert_allclose(o.trace[0]["gbest_x"][a].numpy(), x0[best[a], a].numpy(), rtol=0, atol=1e-6)
+    action = action.cpu()
     assert torch.isfinite(action).all() and (action >= lb).all() and (action <= ub).all()
 
 
