@@ -70,6 +70,10 @@ struct bbmpc_ctx {
   bbmpc::ModelHost model;
   uint64_t launches = 0;
   std::string err;
+  // rollout-kernel timing (bbmpc_profile_*): event pairs recorded around every rollout launch
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;  // [2*i] start, [2*i+1] stop
+  size_t prof_n = 0;                 // pairs recorded since the last read
 };
 
 namespace bbmpc {

@@ -116,13 +116,31 @@ int rollout_dispatch(bbmpc_ctx* ctx, const float* states, const float* actions, 
   if (!ctx->model.set) return fail(ctx, BBMPC_ESTATE, "rollout before a dynamics model was set");
   if (!ctx->reward_id) return fail(ctx, BBMPC_ESTATE, "rollout before a reward function was set");
   const int prec = resolve_precision(ctx);
-  if (prec == BBMPC_PREC_FP32)
-    return launch_rollout_simt(ctx, states, actions, returns, penalty, rows, A, H, 0, st);
-  if (!ctx->model.tc_ok)
+  if (prec != BBMPC_PREC_FP32 && !ctx->model.tc_ok)
     return fail(ctx, BBMPC_EINVAL, "tensor-core precision requested but the model does not fit it: %s",
                 ctx->model.tc_why.c_str());
-  return launch_rollout_tc(ctx, states, actions, returns, penalty, rows, A, H,
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->prof_on) {
+    if (ctx->prof_ev.size() < 2 * (ctx->prof_n + 1)) {
+      cudaEvent_t a, b;
+      BB_CUDA(ctx, cudaEventCreate(&a));
+      BB_CUDA(ctx, cudaEventCreate(&b));
+      ctx->prof_ev.push_back(a); ctx->prof_ev.push_back(b);
+    }
+    e0 = ctx->prof_ev[2 * ctx->prof_n]; e1 = ctx->prof_ev[2 * ctx->prof_n + 1];
+    BB_CUDA(ctx, cudaEventRecord(e0, st));
+  }
+  int rc;
+  if (prec == BBMPC_PREC_FP32)
+    rc = launch_rollout_simt(ctx, states, actions, returns, penalty, rows, A, H, 0, st);
+  else
+    rc = launch_rollout_tc(ctx, states, actions, returns, penalty, rows, A, H,
                            prec == BBMPC_PREC_BF16 ? 1 : 3, st);
+  if (rc == BBMPC_OK && e1) {
+    BB_CUDA(ctx, cudaEventRecord(e1, st));
+    ctx->prof_n++;
+  }
+  return rc;
 }
 
 }  // namespace bbmpc
@@ -165,6 +183,7 @@ void bbmpc_ctx_destroy(bbmpc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   free_model(ctx->model);
   cudaFree(ctx->model.norm_buf);
+  for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -178,6 +197,29 @@ int bbmpc_set_precision(bbmpc_ctx* ctx, int prec) {
 int bbmpc_get_effective_precision(const bbmpc_ctx* ctx) { return ctx ? resolve_precision(ctx) : BBMPC_EINVAL; }
 
 uint64_t bbmpc_launch_count(const bbmpc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int bbmpc_profile_enable(bbmpc_ctx* ctx, int on) {
+  if (!ctx) return BBMPC_EINVAL;
+  ctx->prof_on = on != 0;
+  ctx->prof_n = 0;
+  return BBMPC_OK;
+}
+
+int bbmpc_profile_read(bbmpc_ctx* ctx, double* ms_total, int64_t* n_launches) {
+  if (!ctx) return BBMPC_EINVAL;
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  double total = 0.0;
+  for (size_t i = 0; i < ctx->prof_n; ++i) {
+    BB_CUDA(ctx, cudaEventSynchronize(ctx->prof_ev[2 * i + 1]));
+    float ms = 0.0f;
+    BB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+    total += ms;
+  }
+  if (ms_total) *ms_total = total;
+  if (n_launches) *n_launches = static_cast<int64_t>(ctx->prof_n);
+  ctx->prof_n = 0;
+  return BBMPC_OK;
+}
 
 int bbmpc_model_set_mlp(bbmpc_ctx* ctx, int n_members, int n_layers, const int* dims,
                         const float* const* W, const float* const* b, const int* act_ids, void* stream) {

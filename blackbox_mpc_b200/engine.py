@@ -52,6 +52,15 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.bbmpc_launch_count(self.handle))
 
+    def profile_enable(self, on: bool = True) -> None:
+        self.check(self.lib.bbmpc_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_read(self):
+        """(summed rollout-kernel device time in ms, number of rollout launches) since the last read."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        self.check(self.lib.bbmpc_profile_read(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def stream(self) -> int:
         import torch
         return torch.cuda.current_stream(self.device).cuda_stream

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..sharding import all_gather_partials
 
 
 class OptimizerBase:
@@ -131,11 +132,10 @@ class OptimizerBase:
         if self._world == 1:
             e.check(lib.bbmpc_opt_call(h, _lib.ptr(state), int(time_step), noise, _lib.ptr(action), _lib.ptr(nxt), _lib.ptr(rew), st))
         else:
-            import torch.distributed as dist
             e.check(lib.bbmpc_opt_begin(h, _lib.ptr(state), int(time_step), st))
             for it in range(lib.bbmpc_opt_num_iterations(h)):
                 e.check(lib.bbmpc_opt_iter_local(h, it, _lib.ptr(self._partial), st))
-                dist.all_gather_into_tensor(self._gather_buf, self._partial, group=self._group)
+                all_gather_partials(self._partial, self._gather_buf, group=self._group)
                 e.check(lib.bbmpc_opt_iter_merge(h, it, _lib.ptr(self._gather_buf), self._world, st))
             e.check(lib.bbmpc_opt_finish(h, noise, _lib.ptr(action), _lib.ptr(nxt), _lib.ptr(rew), st))
         return action, nxt, rew

@@ -74,6 +74,11 @@ int bbmpc_set_precision(bbmpc_ctx* ctx, int prec);
 int bbmpc_get_effective_precision(const bbmpc_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t bbmpc_launch_count(const bbmpc_ctx* ctx);
+/* Rollout-kernel timing for bench.py's roofline: while enabled, every rollout launch is bracketed
+ * by a CUDA event pair on its own stream.  bbmpc_profile_read synchronises on the recorded events,
+ * returns the summed device time (ms) and the number of launches, and clears the record. */
+int bbmpc_profile_enable(bbmpc_ctx* ctx, int on);
+int bbmpc_profile_read(bbmpc_ctx* ctx, double* ms_total, int64_t* n_launches);
 
 /* ---- dynamics model: dynamics_functions/deterministic_mlp.py:20-24,49-51 (Dense chain) and
  *      dynamics_handlers/system_dynamics_handler.py:97-161 (process_input / process_output) ---- */

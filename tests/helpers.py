@@ -6,37 +6,9 @@ import oracle
 from blackbox_mpc_b200.utils import workloads
 
 
-def oracle_spaces(w):
-    return oracle.Space(w.lb, w.ub), oracle.Space(-np.ones(w.dS, np.float32), np.ones(w.dS, np.float32))
+from oracle import build as _ob
 
-
-def oracle_evaluator(w, dtype=torch.float32):
-    if w.dynamics == "pendulum_true":
-        handler = oracle.Handler(oracle.PendulumTrueModel(), true_model=True, dtype=dtype)
-    else:
-        members = [oracle.MLP([torch.from_numpy(x) for x in ws], [torch.from_numpy(x) for x in bs], w.activations)
-                   for ws, bs in zip(w.weights, w.biases)]
-        fn = members[0] if len(members) == 1 else oracle.Ensemble(members)
-        handler = oracle.Handler(fn, true_model=False, is_normalized=True, stats=w.stats, dtype=dtype)
-    reward = oracle.pendulum_reward_function if w.reward == "pendulum" else oracle.halfcheetah_reward_function
-    return oracle.Evaluator(reward, handler)
-
-
-ORACLE_OPT = {"CEM": oracle.CEM, "PI2": oracle.PI2, "RandomSearch": oracle.RandomSearch, "PSO": oracle.PSO,
-              "SPSA": oracle.SPSA, "CMA-ES": oracle.CMAES}
-
-
-def oracle_optimizer(w, name=None, dtype=torch.float32, **extra):
-    name = name or w.optimizer_name
-    a_sp, o_sp = oracle_spaces(w)
-    args = dict(w.optimizer_args) if name == w.optimizer_name else {}
-    args.update(planning_horizon=w.planning_horizon, population_size=w.population_size, num_agents=w.num_agents)
-    if name != "RandomSearch":
-        args["max_iterations"] = w.max_iterations or 5
-    args.update(extra)
-    opt = ORACLE_OPT[name](a_sp, o_sp, dtype=dtype, **args)
-    opt.set_trajectory_evaluator(oracle_evaluator(w, dtype))
-    return opt
+oracle_spaces, oracle_evaluator, oracle_optimizer, ORACLE_OPT = _ob.spaces, _ob.evaluator, _ob.optimizer, _ob.OPTIMIZERS
 
 
 def random_actions(w, P, seed=0):
