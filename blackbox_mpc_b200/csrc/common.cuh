@@ -34,6 +34,24 @@ struct LayerDev {
   int64_t img_off;
 };
 
+// One Dense layer of one ensemble member as the MMA issuer of rollout_tc_kernel sees it; the jobs of
+// one horizon step are listed in issue order (same order as the weight chunk table).
+struct TcJob {
+  uint32_t d_col, a_col;   // TMEM columns of the accumulator / of the A operand (hi of K-chunk 0)
+  uint32_t idesc;          // tcgen05 instruction descriptor (M=128, N=Npad, bf16 x bf16 -> f32)
+  uint32_t nchunks;        // K chunks of 16
+  uint32_t desc_lo_base;   // low word of the smem matrix descriptor without the address field (LBO << 16)
+  uint32_t lo_off16;       // (byte offset of the bf16-lo image inside a chunk) >> 4
+  uint32_t flags;          // TCJ_*
+  uint32_t pad;
+};
+enum : uint32_t {
+  TCJ_WAIT_X = 1u,        // first job of a step: wait until the epilogue has written the layer-0 input
+  TCJ_FROM_EPI = 2u,      // A operand is produced chunk-wise by the epilogue (layer l >= 1)
+  TCJ_ACC_FIRST = 4u,     // first MMA accumulates (output layer of ensemble member > 0)
+  TCJ_COMMIT_D0 = 1u << 4, TCJ_COMMIT_D = 2u << 4, TCJ_COMMIT_DOUT = 3u << 4, TCJ_COMMIT_MASK = 3u << 4,
+};
+
 struct MlpDev {
   int n_members, n_layers;
   int64_t w_member_stride, img_member_stride;  // floats / bytes
@@ -42,6 +60,9 @@ struct MlpDev {
   const uint8_t* wimg;   // nullptr when the model does not fit the tensor-core path
   const uint2* chunk_table;  // per step: (byte offset into wimg, bytes) for every chunk in issue order
   int chunks_per_step;
+  int early_l0;    // chunk-table order: first layer of member m+1 issued ahead of the output layer of member m
+  const TcJob* jobs;   // [jobs_per_step]
+  int jobs_per_step;
   int max_width;   // widest activation (incl. input) — SIMT smem sizing
 };
 
@@ -54,6 +75,7 @@ struct ModelHost {
   float* w32_buf = nullptr;
   uint8_t* wimg_buf = nullptr;
   uint2* chunk_table_buf = nullptr;
+  TcJob* jobs_buf = nullptr;
   float* norm_buf = nullptr;
   bool tc_ok = false;
   std::string tc_why;  // why the tensor-core path is unavailable for this model
@@ -70,6 +92,10 @@ struct bbmpc_ctx {
   bbmpc::ModelHost model;
   uint64_t launches = 0;
   std::string err;
+  // few-row step kernel (optimizer tail): per-member partial outputs + arrival counters
+  float* step_scratch = nullptr;
+  unsigned* step_counters = nullptr;
+  void* dbg_host = nullptr;  // BBMPC_DEBUG=1: host-mapped watchdog record of the tensor-core kernel
   // rollout-kernel timing (bbmpc_profile_*): event pairs recorded around every rollout launch
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;  // [2*i] start, [2*i+1] stop
@@ -109,6 +135,8 @@ int launch_rollout_tc(bbmpc_ctx* ctx, const float* states, const float* actions,
                       const float* penalty, int rows, int A, int H, int passes, cudaStream_t st);
 int pack_tc_image(bbmpc_ctx* ctx, cudaStream_t st);   // builds model.wimg from model.w32
 bool tc_supported(const ModelHost& m, std::string* why);
+uint32_t tc_idesc(int Npad);  // instruction descriptor of the rollout kernel's MMAs
+bool tc_column_map(const MlpDev& m, int* buf_w, int* col_x, int* col_dout);  // TMEM budget of the rollout kernel
 int tc_du_slots(int dU);  // action slots at the head of the layer-0 K axis (8 or 16)
 int resolve_precision(const bbmpc_ctx* ctx);
 // rollout dispatch used by bbmpc_rollout and the optimizers.  `penalty` (nullable, [rows]) is

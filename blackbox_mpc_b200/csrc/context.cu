@@ -2,6 +2,7 @@
 // evaluator-level C-ABI entry points.
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "device_fns.cuh"
@@ -82,15 +83,12 @@ bool tc_supported(const ModelHost& m, std::string* why) {
   if (m.dyn_id != BBMPC_DYN_MLP) return no("analytical dynamics has no GEMM");
   const MlpDev& p = m.mlp;
   if (m.dS > 32 || m.dU > 16) return no("dS > 32 or dU > 16");
-  int d_main = 0, a_cols = 0;
   for (int l = 0; l < p.n_layers; ++l) {
     const LayerDev& L = p.layer[l];
     if (L.Npad > 256 || L.Kpad > 256) return no("layer wider than 253");
-    if (l < p.n_layers - 1 && L.Npad > d_main) d_main = L.Npad;
-    if (l > 0 && L.Kpad > a_cols) a_cols = L.Kpad;
   }
-  const int total = d_main + p.layer[p.n_layers - 1].Npad + p.layer[0].Kpad + a_cols;
-  if (total > 512) return no("TMEM budget exceeded (D + Dout + X + A > 512 columns)");
+  if (!tc_column_map(p, nullptr, nullptr, nullptr))
+    return no("TMEM budget exceeded (hidden width + 3 must pad to <= 224 columns)");
   if (p.layer[p.n_layers - 1].N != m.dS) return no("output width != dS");
   if (p.n_members > 1 && p.layer[p.n_layers - 1].act != BBMPC_ACT_NONE)
     return no("ensemble with a non-linear output layer");
@@ -104,8 +102,8 @@ int resolve_precision(const bbmpc_ctx* ctx) {
 }
 
 static void free_model(ModelHost& m) {
-  cudaFree(m.w32_buf); cudaFree(m.wimg_buf); cudaFree(m.chunk_table_buf);
-  m.w32_buf = nullptr; m.wimg_buf = nullptr; m.chunk_table_buf = nullptr;
+  cudaFree(m.w32_buf); cudaFree(m.wimg_buf); cudaFree(m.chunk_table_buf); cudaFree(m.jobs_buf);
+  m.w32_buf = nullptr; m.wimg_buf = nullptr; m.chunk_table_buf = nullptr; m.jobs_buf = nullptr;
   m.mlp = MlpDev{};
   m.tc_ok = false;
   m.set = false;
@@ -183,6 +181,8 @@ void bbmpc_ctx_destroy(bbmpc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   free_model(ctx->model);
   cudaFree(ctx->model.norm_buf);
+  cudaFree(ctx->step_scratch); cudaFree(ctx->step_counters);
+  if (ctx->dbg_host) cudaFreeHost(ctx->dbg_host);
   for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
   delete ctx;
 }
@@ -292,13 +292,52 @@ int bbmpc_model_set_mlp(bbmpc_ctx* ctx, int n_members, int n_layers, const int* 
                                                        m.wimg_buf + io, L.K, L.N, L.ldw, L.Kpad, L.Npad,
                                                        l == 0 ? tc_du_slots(m.dU) : 0, m.dS, m.dU);
         BB_LAUNCH_CHECK(ctx);
-        for (int c = 0; c < L.Kpad / 16; ++c)
-          table.push_back(make_uint2(static_cast<uint32_t>(io + static_cast<int64_t>(c) * L.chunk_bytes),
-                                     static_cast<uint32_t>(L.chunk_bytes)));
       }
+    // chunk table in the MMA issue order of rollout_tc_kernel (run_layer): L0(0); per member: hidden
+    // layers 1..nL-2, L0(next member), output layer.
+    std::vector<TcJob> jobs;
+    int buf_w = 0, col_x = 0, col_dout = 0;
+    tc_column_map(p, &buf_w, &col_x, &col_dout);
+    auto push_layer = [&](int mm, int l) {
+      const LayerDev& L = p.layer[l];
+      const int64_t io = L.img_off + mm * p.img_member_stride;
+      for (int c = 0; c < L.Kpad / 16; ++c)
+        table.push_back(make_uint2(static_cast<uint32_t>(io + static_cast<int64_t>(c) * L.chunk_bytes),
+                                   static_cast<uint32_t>(L.chunk_bytes)));
+      const bool last = (l == n_layers - 1);
+      const int idx = mm * (n_layers - 1) + l;   // running index of hidden accumulators: TMEM buffer = idx & 1
+      TcJob j{};
+      j.d_col = last ? col_dout : ((idx & 1) ? 256 : 0);
+      j.a_col = l == 0 ? col_x : (((idx - 1) & 1) ? 256 : 0);
+      j.idesc = tc_idesc(L.Npad);
+      j.nchunks = L.Kpad / 16;
+      const uint32_t kstep = static_cast<uint32_t>(L.Npad) * 16;  // bytes between the two 8-wide K slabs of a chunk
+      j.desc_lo_base = ((kstep >> 4) & 0x3FFF) << 16;
+      j.lo_off16 = (2 * kstep) >> 4;
+      j.flags = (l == 0 && mm == 0 ? TCJ_WAIT_X : 0u) | (l > 0 ? TCJ_FROM_EPI : 0u) | (last && mm > 0 ? TCJ_ACC_FIRST : 0u) |
+                (!last ? (l == 0 ? TCJ_COMMIT_D0 : TCJ_COMMIT_D) : (mm == n_members - 1 ? TCJ_COMMIT_DOUT : 0u));
+      jobs.push_back(j);
+    };
+    if (n_layers == 1) {
+      for (int mm = 0; mm < n_members; ++mm) push_layer(mm, 0);
+    } else {
+      const bool early = getenv("BBMPC_NO_EARLY_L0") == nullptr;
+      p.early_l0 = early ? 1 : 0;
+      if (early) push_layer(0, 0);
+      for (int mm = 0; mm < n_members; ++mm) {
+        if (!early) push_layer(mm, 0);
+        for (int l = 1; l + 1 < n_layers; ++l) push_layer(mm, l);
+        if (early && mm + 1 < n_members) push_layer(mm + 1, 0);
+        push_layer(mm, n_layers - 1);
+      }
+    }
     BB_CUDA(ctx, cudaMalloc(&m.chunk_table_buf, table.size() * sizeof(uint2)));
     BB_CUDA(ctx, cudaMemcpyAsync(m.chunk_table_buf, table.data(), table.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
-    BB_CUDA(ctx, cudaStreamSynchronize(st));  // `table` is a stack-lifetime host buffer
+    BB_CUDA(ctx, cudaMalloc(&m.jobs_buf, jobs.size() * sizeof(TcJob)));
+    BB_CUDA(ctx, cudaMemcpyAsync(m.jobs_buf, jobs.data(), jobs.size() * sizeof(TcJob), cudaMemcpyHostToDevice, st));
+    BB_CUDA(ctx, cudaStreamSynchronize(st));  // `table` / `jobs` are stack-lifetime host buffers
+    p.jobs = m.jobs_buf;
+    p.jobs_per_step = static_cast<int>(jobs.size());
     p.wimg = m.wimg_buf;
     p.chunk_table = m.chunk_table_buf;
     p.chunks_per_step = static_cast<int>(table.size());

@@ -92,6 +92,14 @@ __device__ __forceinline__ float act_fast(float v, int act) {
   }
 }
 
+template <int ACT>
+__device__ __forceinline__ float act_fast_t(float v) {
+  if (ACT == BBMPC_ACT_TANH) return tanh_fast(v);
+  if (ACT == BBMPC_ACT_RELU) return fmaxf(v, 0.0f);
+  if (ACT == BBMPC_ACT_SIGMOID) return fmaf(0.5f, tanh_fast(0.5f * v), 0.5f);
+  return v;
+}
+
 // ----------------------------------------------------------------------------- analytical dynamics
 // utils/pendulum.py:78-92.  x = [cos th, sin th, thdot, u]; writes the DEVIATION new - s.
 // g=10, m=l=1, dt=.05; thdot clipped to +-8 AFTER newth is formed; u is not clipped.

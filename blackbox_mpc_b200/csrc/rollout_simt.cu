@@ -217,6 +217,84 @@ __global__ void __launch_bounds__(TR* NG) step_simt_kernel(const SimtParams p) {
   if ((mode & 2) && g == 0 && valid) p.io.reward_out[row] = row_reward(p, sm, lane);
 }
 
+// Few-row variant of step_simt_kernel for the optimizer tail (optimizers/optimizer_base.py:91-94:
+// A rows) and small predict/forward calls.  One CTA per (row, ensemble member), thread = output
+// feature, so the serial K loop of a layer is spread over up to 256 coalesced weight streams
+// instead of one lane per row.  Same fp32 arithmetic and summation order as dense_layer().  The
+// last CTA to finish a row (arrival counter) sums the members in member order and applies
+// process_output + reward.
+constexpr int STEP_THREADS = 256;
+constexpr int STEP_MAX_ROWS = 64;
+__global__ void __launch_bounds__(STEP_THREADS) step_mlp_kernel(const SimtParams p, float* __restrict__ scratch,
+                                                               unsigned* __restrict__ counters) {
+  extern __shared__ float smem_f[];
+  __shared__ bool is_last;
+  const MlpDev& m = p.mlp;
+  const int b = blockIdx.x, mm = blockIdx.y, tid = threadIdx.x;
+  const int dS = p.dS, dU = p.dU, mode = p.io.mode;
+  const bool norm_on = p.norm.enabled;
+  float* in = smem_f;
+  float* out = smem_f + m.max_width;
+  for (int k = tid; k < dS + dU; k += STEP_THREADS) {
+    float v;
+    if (mode & 4) {
+      v = p.io.s[static_cast<size_t>(b) * (dS + dU) + k];
+    } else if (k < dS) {
+      v = p.io.s[static_cast<size_t>(b) * dS + k];
+      if (norm_on) v = __fdiv_rn(__fsub_rn(v, p.norm.mean_s[k]), p.norm.den_s[k]);
+    } else {
+      v = p.io.a[static_cast<size_t>(b) * dU + (k - dS)];
+      if (norm_on) v = __fdiv_rn(__fsub_rn(v, p.norm.mean_a[k - dS]), p.norm.den_a[k - dS]);
+    }
+    in[k] = v;
+  }
+  __syncthreads();
+  for (int l = 0; l < m.n_layers; ++l) {
+    const LayerDev& L = m.layer[l];
+    const bool last = (l == m.n_layers - 1);
+    const float* __restrict__ W = m.w32 + L.w_off + mm * m.w_member_stride;
+    const float* __restrict__ bias = m.w32 + L.b_off + mm * m.w_member_stride;
+    for (int f = tid; f < L.N; f += STEP_THREADS) {
+      float acc = 0.0f;
+#pragma unroll 8
+      for (int k = 0; k < L.K; ++k) acc = fmaf(in[k], __ldg(W + static_cast<size_t>(k) * L.ldw + f), acc);
+      const float v = act_exact(__fadd_rn(acc, __ldg(bias + f)), L.act);
+      if (last) scratch[(static_cast<size_t>(b) * m.n_members + mm) * dS + f] = v;
+      else out[f] = v;
+    }
+    __syncthreads();
+    float* t = in; in = out; out = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(&counters[b], 1u) == static_cast<unsigned>(m.n_members - 1));
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (tid == 0) counters[b] = 0;  // self-resetting for the next launch
+  float* s2s = smem_f;            // [dS]
+  for (int i = tid; i < dS; i += STEP_THREADS) {
+    float y = __ldcg(scratch + (static_cast<size_t>(b) * m.n_members) * dS + i);
+    for (int k = 1; k < m.n_members; ++k) y = __fadd_rn(y, __ldcg(scratch + (static_cast<size_t>(b) * m.n_members + k) * dS + i));
+    if (m.n_members > 1) y = __fdiv_rn(y, static_cast<float>(m.n_members));
+    if (mode & 4) {
+      p.io.raw_out[static_cast<size_t>(b) * dS + i] = y;
+    } else {
+      const float d = norm_on ? __fadd_rn(p.norm.mean_t[i], __fmul_rn(y, p.norm.den_t[i])) : y;
+      const float s2 = __fadd_rn(d, p.io.s[static_cast<size_t>(b) * dS + i]);
+      s2s[i] = s2;
+      if (p.io.s2_out) p.io.s2_out[static_cast<size_t>(b) * dS + i] = s2;
+    }
+  }
+  __syncthreads();
+  if ((mode & 2) && tid == 0) {
+    float s[MAX_DS], s2[MAX_DS], a[MAX_DU];
+    for (int i = 0; i < dS; ++i) { s[i] = p.io.s[static_cast<size_t>(b) * dS + i]; s2[i] = s2s[i]; }
+    for (int i = 0; i < dU; ++i) a[i] = p.io.a[static_cast<size_t>(b) * dU + i];
+    p.io.reward_out[b] = reward_dispatch(p.reward_id, s, a, s2, dS, dU);
+  }
+}
+
 static int fill_params(bbmpc_ctx* ctx, SimtParams& p) {
   const ModelHost& m = ctx->model;
   p.mlp = m.mlp; p.norm = m.norm; p.dyn_id = m.dyn_id; p.reward_id = ctx->reward_id; p.dS = m.dS; p.dU = m.dU;
@@ -255,6 +333,17 @@ int launch_step_simt(bbmpc_ctx* ctx, const StepIO& io, cudaStream_t st) {
   if (int rc = fill_params(ctx, p)) return rc;
   p.io = io;
   const int grid = (io.B + TR - 1) / TR;
+  if (p.dyn_id == BBMPC_DYN_MLP && ctx->model.set && io.B <= STEP_MAX_ROWS && (io.mode & 5)) {
+    if (!ctx->step_scratch) {
+      BB_CUDA(ctx, cudaMalloc(&ctx->step_scratch, sizeof(float) * STEP_MAX_ROWS * MAX_MEMBERS * MAX_DS));
+      BB_CUDA(ctx, cudaMalloc(&ctx->step_counters, sizeof(unsigned) * STEP_MAX_ROWS));
+      BB_CUDA(ctx, cudaMemset(ctx->step_counters, 0, sizeof(unsigned) * STEP_MAX_ROWS));
+    }
+    const size_t sb = sizeof(float) * 2 * static_cast<size_t>(p.mlp.max_width > MAX_DS ? p.mlp.max_width : MAX_DS);
+    step_mlp_kernel<<<dim3(io.B, p.mlp.n_members), STEP_THREADS, sb, st>>>(p, ctx->step_scratch, ctx->step_counters);
+    BB_LAUNCH_CHECK(ctx);
+    return BBMPC_OK;
+  }
   if (p.dyn_id == BBMPC_DYN_MLP && ctx->model.set) {
     const size_t sb = simt_smem_bytes(p.dS, p.dU, p.mlp.max_width);
     if (int rc = set_smem(ctx, step_simt_kernel<BBMPC_DYN_MLP>, sb)) return rc;

@@ -49,11 +49,31 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 #endif
 // Blocks until the phase with the given parity completes.  Traps after a bounded number of
 // polls so a broken pipeline aborts the launch (sticky error on the host) instead of hanging.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// When TC05_DEBUG_BUF is defined it names a `volatile uint32_t*` in scope (host-mapped memory): the
+// watchdog records which barrier/parity/thread starved before trapping.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile uint32_t* dbg = nullptr,
+                                          uint32_t tag = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > TC05_WATCHDOG_SPINS) { asm volatile("trap;"); }
+    ++spins;
+    if (dbg && spins == TC05_WATCHDOG_SPINS / 2 && (threadIdx.x & 31) == 0) {
+      const uint32_t slot = 8u * (threadIdx.x >> 5) + 128u * (blockIdx.x & 1);
+      dbg[slot + 0] = 0xDEAD0000u | threadIdx.x; dbg[slot + 1] = bar; dbg[slot + 2] = parity; dbg[slot + 3] = tag;
+      __threadfence_system();
+    }
+    if (spins > TC05_WATCHDOG_SPINS) { asm volatile("trap;"); }
   }
+}
+
+// One lane of a fully converged warp (the same lane every time): predicate for single-thread issue.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ----------------------------------------------------------------------------- bulk copy (UBLKCP)
