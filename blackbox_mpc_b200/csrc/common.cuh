@@ -28,9 +28,12 @@ struct NormDev {
 struct LayerDev {
   int K, N, ldw, act;
   int64_t w_off, b_off;  // member 0; member m adds m * MlpDev::w_member_stride
-  // tensor-core image: Kpad/16 chunks per (member, layer); chunk c of member m starts at
-  // img_off + m*img_member_stride + c*chunk_bytes and holds [hi: 2 x Npad x 16B][lo: 2 x Npad x 16B].
-  int Kpad, Npad, chunk_bytes;
+  // tensor-core image.  The N axis of a hidden layer is cut at column `nsplit` (a multiple of 32, 0 =
+  // not cut) into two column ranges ("halves") that are contracted as separate MMA jobs, so that the
+  // epilogue can convert the first range while the tensor pipe still works on the second.  Per
+  // (member, layer) the image is [half 0: Kpad/16 chunks][half 1: Kpad/16 chunks]; a chunk of a half
+  // with Nh columns holds [hi: 2 K-slabs x Nh x 16B][lo: 2 x Nh x 16B] (K-major 8x16B core matrices).
+  int Kpad, Npad, nsplit;
   int64_t img_off;
 };
 
@@ -43,13 +46,21 @@ struct TcJob {
   uint32_t desc_lo_base;   // low word of the smem matrix descriptor without the address field (LBO << 16)
   uint32_t lo_off16;       // (byte offset of the bf16-lo image inside a chunk) >> 4
   uint32_t flags;          // TCJ_*
-  uint32_t pad;
+  uint32_t chunk16;        // chunk_bytes >> 4: distance between consecutive K-chunks inside a ring stage
+  uint32_t ngroups;        // the job's chunks reach shared memory in `ngroups` ring stages ...
+  uint32_t gsz;            // ... of gsz[4*g +: 4] UNITS (pairs of K-chunks) each: one bulk copy, one full/empty barrier pair per group
+  uint32_t pad[2];
 };
+constexpr int TC_GROUP_CAP_BYTES = 53248;  // ring-stage capacity target (4 K-chunks of a 208-wide layer)
+constexpr int TC_MAX_GROUPS = 8;
 enum : uint32_t {
   TCJ_WAIT_X = 1u,        // first job of a step: wait until the epilogue has written the layer-0 input
   TCJ_FROM_EPI = 2u,      // A operand is produced chunk-wise by the epilogue (layer l >= 1)
   TCJ_ACC_FIRST = 4u,     // first MMA accumulates (output layer of ensemble member > 0)
-  TCJ_COMMIT_D0 = 1u << 4, TCJ_COMMIT_D = 2u << 4, TCJ_COMMIT_DOUT = 3u << 4, TCJ_COMMIT_MASK = 3u << 4,
+  TCJ_ROUND_END = 8u,     // last job that reads the current A-operand round (flips the unit-barrier set)
+  // completion barrier of the job: first-layer / later hidden layer x column half, or the output accumulator
+  TCJ_COMMIT_D0H0 = 1u << 4, TCJ_COMMIT_D0H1 = 2u << 4, TCJ_COMMIT_DH0 = 3u << 4, TCJ_COMMIT_DH1 = 4u << 4,
+  TCJ_COMMIT_DOUT = 5u << 4, TCJ_COMMIT_MASK = 7u << 4,
 };
 
 struct MlpDev {
@@ -58,8 +69,9 @@ struct MlpDev {
   LayerDev layer[MAX_LAYERS];
   const float* w32;
   const uint8_t* wimg;   // nullptr when the model does not fit the tensor-core path
-  const uint2* chunk_table;  // per step: (byte offset into wimg, bytes) for every chunk in issue order
-  int chunks_per_step;
+  const uint2* chunk_table;  // per step: (byte offset into wimg, bytes) of every chunk GROUP in issue order
+  int chunks_per_step;       // number of groups per step
+  int stage_bytes;           // largest group
   int early_l0;    // chunk-table order: first layer of member m+1 issued ahead of the output layer of member m
   const TcJob* jobs;   // [jobs_per_step]
   int jobs_per_step;

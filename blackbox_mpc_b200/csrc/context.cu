@@ -32,14 +32,14 @@ __global__ void copy_pad_kernel(const float* __restrict__ src, float* __restrict
   dst[i] = n < N ? src[static_cast<size_t>(k) * N + n] : 0.0f;
 }
 
-// Tensor-core image of one (member, layer): weight rows split hi + lo; three rows hold the bias as
+// Tensor-core image of one (member, layer): weight rows (times `scale`) split hi + lo; three rows hold the bias as
 // bf16 terms (b = b1 + b2 + b3 to 24 bits) that meet ones-columns of the A operand; the rest is
 // zero.  Image row order: hidden layers [w_0..w_{K-1} | bias x3]; layer 0 (du_slots > 0) is
 // [action rows padded to du_slots | state rows | bias x3] so that the epilogue can assemble its
 // input with compile-time register indices.
 __global__ void pack_tc_kernel(const float* __restrict__ W, const float* __restrict__ b,
-                               uint8_t* __restrict__ img, int K, int N, int ldw, int Kpad, int Npad,
-                               int du_slots, int dS, int dU) {
+                               uint8_t* __restrict__ img, int K, int N, int ldw, int Kpad, int Npad, int nsplit,
+                               int du_slots, int dS, int dU, float scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Kpad * Npad) return;
   const int k = i / Npad, n = i % Npad;
@@ -55,21 +55,24 @@ __global__ void pack_tc_kernel(const float* __restrict__ W, const float* __restr
   __nv_bfloat16 hi = __float2bfloat16(0.0f), lo = hi;
   if (n < N) {
     if (src >= 0) {
-      const float v = W[static_cast<size_t>(src) * ldw + n];
+      const float v = __fmul_rn(W[static_cast<size_t>(src) * ldw + n], scale);
       hi = __float2bfloat16_rn(v);
       lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     } else if (bias_term >= 0) {
-      float r = b[n];
+      float r = __fmul_rn(b[n], scale);
       __nv_bfloat16 t = __float2bfloat16_rn(r);
       for (int j = 0; j < bias_term; ++j) { r -= __bfloat162float(t); t = __float2bfloat16_rn(r); }
       hi = t;
     }
   }
   const int chunk = k >> 4, kk = k & 15;
-  const size_t chunk_bytes = static_cast<size_t>(Npad) * 64;
-  const size_t off = chunk * chunk_bytes + (static_cast<size_t>(kk >> 3) * Npad + n) * 16 + (kk & 7) * 2;
+  const bool second = nsplit > 0 && n >= nsplit;
+  const int Nh = nsplit > 0 ? (second ? Npad - nsplit : nsplit) : Npad;
+  const int nh = second ? n - nsplit : n;
+  const size_t half_base = second ? static_cast<size_t>(Kpad / 16) * nsplit * 64 : 0;
+  const size_t off = half_base + static_cast<size_t>(chunk) * Nh * 64 + (static_cast<size_t>(kk >> 3) * Nh + nh) * 16 + (kk & 7) * 2;
   *reinterpret_cast<__nv_bfloat16*>(img + off) = hi;
-  *reinterpret_cast<__nv_bfloat16*>(img + off + static_cast<size_t>(Npad) * 32) = lo;
+  *reinterpret_cast<__nv_bfloat16*>(img + off + static_cast<size_t>(Nh) * 32) = lo;
 }
 
 __global__ void norm_prepare_kernel(const float* __restrict__ std_in, float* __restrict__ den, int n) {
@@ -251,11 +254,14 @@ int bbmpc_model_set_mlp(bbmpc_ctx* ctx, int n_members, int n_layers, const int* 
     if (L.act < BBMPC_ACT_NONE || L.act > BBMPC_ACT_SIGMOID) return fail(ctx, BBMPC_EINVAL, "unknown activation id %d", L.act);
     L.Kpad = round_up((l == 0 ? L.K - m.dU + tc_du_slots(m.dU) : L.K) + BIAS_COLS, 16);
     L.Npad = round_up(L.N, 16);
-    L.chunk_bytes = L.Npad * 64;
+    // Optional (BBMPC_NSPLIT=1): hidden layers wide enough are cut into two column ranges at a multiple of 32
+    // (whole epilogue units).  Measured slower than the unsplit pipeline on B200 (r1c: 1.90 vs 1.73 ms per
+    // C4 rollout): the extra handoffs cost more than the overlap gains while the epilogue is MUFU-bound.
+    L.nsplit = (l + 1 < n_layers && L.Npad >= 64 && getenv("BBMPC_NSPLIT")) ? (L.Npad / 32) * 16 : 0;
     if (L.N > p.max_width) p.max_width = L.N;
     L.w_off = w_floats; w_floats += static_cast<int64_t>(L.K) * L.ldw;
     L.b_off = w_floats; w_floats += L.ldw;
-    L.img_off = img_bytes; img_bytes += static_cast<int64_t>(L.Kpad / 16) * L.chunk_bytes;
+    L.img_off = img_bytes; img_bytes += static_cast<int64_t>(L.Kpad / 16) * L.Npad * 64;
   }
   p.w_member_stride = w_floats;
   p.img_member_stride = img_bytes;
@@ -289,8 +295,10 @@ int bbmpc_model_set_mlp(bbmpc_ctx* ctx, int n_members, int n_layers, const int* 
         const int64_t io = L.img_off + mm * p.img_member_stride;
         pack_tc_kernel<<<(n + 255) / 256, 256, 0, st>>>(m.w32_buf + L.w_off + mm * p.w_member_stride,
                                                        m.w32_buf + L.b_off + mm * p.w_member_stride,
-                                                       m.wimg_buf + io, L.K, L.N, L.ldw, L.Kpad, L.Npad,
-                                                       l == 0 ? tc_du_slots(m.dU) : 0, m.dS, m.dU);
+                                                       m.wimg_buf + io, L.K, L.N, L.ldw, L.Kpad, L.Npad, L.nsplit,
+                                                       l == 0 ? tc_du_slots(m.dU) : 0, m.dS, m.dU,
+                                                       // hidden tanh layers deliver 2 log2(e) x: the epilogue's tanh starts at ex2
+                                                       (l + 1 < n_layers && L.act == BBMPC_ACT_TANH) ? 2.8853900817779268f : 1.0f);
         BB_LAUNCH_CHECK(ctx);
       }
     // chunk table in the MMA issue order of rollout_tc_kernel (run_layer): L0(0); per member: hidden
@@ -298,25 +306,56 @@ int bbmpc_model_set_mlp(bbmpc_ctx* ctx, int n_members, int n_layers, const int* 
     std::vector<TcJob> jobs;
     int buf_w = 0, col_x = 0, col_dout = 0;
     tc_column_map(p, &buf_w, &col_x, &col_dout);
+    int stage_bytes = 0;
+    // One job per (member, layer, column half), in MMA issue order.
     auto push_layer = [&](int mm, int l) {
       const LayerDev& L = p.layer[l];
-      const int64_t io = L.img_off + mm * p.img_member_stride;
-      for (int c = 0; c < L.Kpad / 16; ++c)
-        table.push_back(make_uint2(static_cast<uint32_t>(io + static_cast<int64_t>(c) * L.chunk_bytes),
-                                   static_cast<uint32_t>(L.chunk_bytes)));
+      const int nch = L.Kpad / 16;
+      const int nunits = (nch + 1) / 2;
       const bool last = (l == n_layers - 1);
       const int idx = mm * (n_layers - 1) + l;   // running index of hidden accumulators: TMEM buffer = idx & 1
-      TcJob j{};
-      j.d_col = last ? col_dout : ((idx & 1) ? 256 : 0);
-      j.a_col = l == 0 ? col_x : (((idx - 1) & 1) ? 256 : 0);
-      j.idesc = tc_idesc(L.Npad);
-      j.nchunks = L.Kpad / 16;
-      const uint32_t kstep = static_cast<uint32_t>(L.Npad) * 16;  // bytes between the two 8-wide K slabs of a chunk
-      j.desc_lo_base = ((kstep >> 4) & 0x3FFF) << 16;
-      j.lo_off16 = (2 * kstep) >> 4;
-      j.flags = (l == 0 && mm == 0 ? TCJ_WAIT_X : 0u) | (l > 0 ? TCJ_FROM_EPI : 0u) | (last && mm > 0 ? TCJ_ACC_FIRST : 0u) |
-                (!last ? (l == 0 ? TCJ_COMMIT_D0 : TCJ_COMMIT_D) : (mm == n_members - 1 ? TCJ_COMMIT_DOUT : 0u));
-      jobs.push_back(j);
+      const int n_halves = L.nsplit > 0 ? 2 : 1;
+      for (int h = 0; h < n_halves; ++h) {
+        const int n0 = h ? L.nsplit : 0;
+        const int Nh = L.nsplit > 0 ? (h ? L.Npad - L.nsplit : L.nsplit) : L.Npad;
+        const int chunk_bytes = Nh * 64;
+        const int64_t io = L.img_off + mm * p.img_member_stride + (h ? static_cast<int64_t>(nch) * L.nsplit * 64 : 0);
+        // groups of whole UNITS (pairs of K-chunks): one ring stage / bulk copy / barrier pair each
+        int gmax = TC_GROUP_CAP_BYTES / (2 * chunk_bytes);
+        if (gmax < 1) gmax = 1;
+        if (gmax > 15) gmax = 15;
+        int ngroups = (nunits + gmax - 1) / gmax;
+        if (ngroups > TC_MAX_GROUPS) ngroups = TC_MAX_GROUPS;
+        uint32_t gsz = 0;
+        int u0 = 0;
+        for (int g = 0; g < ngroups; ++g) {
+          const int nu = (nunits - u0 + (ngroups - g) - 1) / (ngroups - g);   // balanced split
+          const int c0 = 2 * u0, c1 = (2 * (u0 + nu) < nch) ? 2 * (u0 + nu) : nch;
+          table.push_back(make_uint2(static_cast<uint32_t>(io + static_cast<int64_t>(c0) * chunk_bytes),
+                                     static_cast<uint32_t>((c1 - c0) * chunk_bytes)));
+          if ((c1 - c0) * chunk_bytes > stage_bytes) stage_bytes = (c1 - c0) * chunk_bytes;
+          gsz |= static_cast<uint32_t>(nu) << (4 * g);
+          u0 += nu;
+        }
+        TcJob j{};
+        j.d_col = (last ? col_dout : ((idx & 1) ? 256 : 0)) + n0;
+        j.a_col = l == 0 ? col_x : (((idx - 1) & 1) ? 256 : 0);
+        j.idesc = tc_idesc(Nh);
+        j.nchunks = nch;
+        const uint32_t kstep = static_cast<uint32_t>(Nh) * 16;  // bytes between the two 8-wide K slabs of a chunk
+        j.desc_lo_base = ((kstep >> 4) & 0x3FFF) << 16;
+        j.lo_off16 = (2 * kstep) >> 4;
+        j.chunk16 = static_cast<uint32_t>(chunk_bytes) >> 4;
+        j.ngroups = ngroups;
+        j.gsz = gsz;
+        uint32_t commit;
+        if (last) commit = (mm == n_members - 1) ? TCJ_COMMIT_DOUT : 0u;
+        else if (l == 0) commit = h ? TCJ_COMMIT_D0H1 : TCJ_COMMIT_D0H0;
+        else commit = h ? TCJ_COMMIT_DH1 : TCJ_COMMIT_DH0;
+        j.flags = (l == 0 && mm == 0 && h == 0 ? TCJ_WAIT_X : 0u) | (l > 0 && h == 0 ? TCJ_FROM_EPI : 0u) |
+                  (l > 0 && h == n_halves - 1 ? TCJ_ROUND_END : 0u) | (last && mm > 0 ? TCJ_ACC_FIRST : 0u) | commit;
+        jobs.push_back(j);
+      }
     };
     if (n_layers == 1) {
       for (int mm = 0; mm < n_members; ++mm) push_layer(mm, 0);
@@ -341,6 +380,7 @@ int bbmpc_model_set_mlp(bbmpc_ctx* ctx, int n_members, int n_layers, const int* 
     p.wimg = m.wimg_buf;
     p.chunk_table = m.chunk_table_buf;
     p.chunks_per_step = static_cast<int>(table.size());
+    p.stage_bytes = stage_bytes;
   }
   return BBMPC_OK;
 }

@@ -29,6 +29,7 @@
 // tile (accumulate flag), the epilogue divides by n_members.
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 #include "common.cuh"
 #include "device_fns.cuh"
 #include "tc05.cuh"
@@ -36,8 +37,13 @@
 namespace bbmpc {
 using namespace tc05;
 
-constexpr int TC_THREADS = 320;
-constexpr int EPI_WARPS = 8;
+static_assert(true, "");
+constexpr int EPI_SUB = 4;                      // conversion warps per TMEM lane quarter
+constexpr int EPI_WARPS = 4 * EPI_SUB;
+constexpr int TC_WARPS = 8 + EPI_WARPS;         // warpgroup 0: producer, MMA issuer, TMEM owner, idle; warpgroup 1: state warps
+constexpr int TC_THREADS = 32 * TC_WARPS;
+// (768 threads -> 80 registers per thread; ptxas does not raise the cap after setmaxnreg.inc, so every
+// role is written to fit 80 registers and no setmaxnreg is used.)
 constexpr int TC_MAX_STAGES = 24;
 constexpr int TC_MAX_CHUNKS = 16;   // K chunks of one layer (Kpad <= 256)
 constexpr int TILE_ROWS = 128;
@@ -51,68 +57,145 @@ struct TcParams {
   int stage_bytes, n_stages;
   int col_buf0, col_buf1, col_x, col_dout;  // TMEM column map
   uint32_t* dbg;  // host-mapped watchdog record (BBMPC_DEBUG=1), else nullptr
+  uint32_t* trace; // BBMPC_TC_TRACE: per-warp (tag, clock) records of CTA 0, step 1
+  int xflags;     // BBMPC_TC_X timing experiments (results are garbage): 1 = no weight loads, 2 = identity activations
 };
 
 struct TcSmemLayout {
-  uint32_t stages, table, jobs, bars, tmem_slot, stats, total;
+  uint32_t stages, table, jobs, bars, tmem_slot, stats, conv, total;
 };
-constexpr int TC_NUM_BARS = 2 * TC_MAX_STAGES + 2 * TC_MAX_CHUNKS + 4;
-__host__ __device__ inline TcSmemLayout tc_layout(int stage_bytes, int n_stages, int chunks_per_step, int jobs_per_step) {
+constexpr int TC_NUM_BARS = 2 * TC_MAX_STAGES + 2 * TC_MAX_CHUNKS + 6;
+__host__ __device__ inline TcSmemLayout tc_layout(int stage_bytes, int n_stages, int groups_per_step, int jobs_per_step) {
   TcSmemLayout L;
   uint32_t off = 0;
   L.stages = off; off += static_cast<uint32_t>(stage_bytes) * n_stages;
-  L.table = off;  off += static_cast<uint32_t>(chunks_per_step) * 8;
+  L.table = off;  off += static_cast<uint32_t>(groups_per_step) * 8;
   off = (off + 15u) & ~15u;
   L.jobs = off;   off += static_cast<uint32_t>(jobs_per_step) * sizeof(TcJob);
   L.bars = off;   off += TC_NUM_BARS * 8;
   L.tmem_slot = off; off += 16;
   L.stats = off;  off += (4 * MAX_DS + 2 * MAX_DU) * 4;
+  L.conv = off;   off += MAX_LAYERS * 32;
   L.total = off;
   return L;
 }
 
-// One hidden-layer epilogue of one thread: accumulator chunks c = half, half+2, ... of its TMEM
-// lane -> activation -> bf16 hi/lo -> written back over the same 16 columns -> chunk published.
+template <bool ON>
+struct Tracer {
+  uint32_t* buf; uint32_t n; bool on;
+  __device__ __forceinline__ void rec(uint32_t tag) {
+    if (ON) { if (on && n < 500) { buf[2 * n] = tag; buf[2 * n + 1] = static_cast<uint32_t>(clock64()); ++n; } }
+  }
+  __device__ __forceinline__ void arm(bool v) { if (ON) on = v; }
+};
+
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {  // non-blocking probe
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+
+// tanh of two pre-activations that arrive PRE-SCALED by 2 log2(e) (the scale is folded into the
+// layer's weight image, see pack_tc_kernel): w = 2^-|t| in (0,1], tanh|x| = 2/(1+w) - 1.  The two
+// reciprocals share ONE MUFU.RCP: r = 1/((1+w0)(1+w1)) (product <= 4, no overflow), 1/(1+w0) =
+// r (1+w1).  3 MUFU per pair instead of 4; absolute error <= ~3e-7, far below the 2^-17 relative
+// error of the bf16 hi+lo operand split downstream.  NaN propagates through ex2.
+__device__ __forceinline__ void tanh_pair_prescaled(float& x0, float& x1) {
+  float w0, w1, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w0) : "f"(-fabsf(x0)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w1) : "f"(-fabsf(x1)));
+  const float d0 = w0 + 1.0f, d1 = w1 + 1.0f;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d0 * d1));
+  const float y0 = fmaf(r * d1, 2.0f, -1.0f), y1 = fmaf(r * d0, 2.0f, -1.0f);
+  // copysign: (y & ~sign) | (x & sign) in one LOP3
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD8;" : "=f"(x0) : "f"(y0), "f"(x0));
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD8;" : "=f"(x1) : "f"(y1), "f"(x1));
+}
+
 template <int ACT>
-__device__ __forceinline__ void epi_hidden(uint32_t taddr, int Npad, int N, int n_a_chunks, int half, int passes,
-                                           uint32_t bar_achunk, int lane) {
-  for (int c = half; c < n_a_chunks; c += 2) {
-    float v[16];
-    if (16 * c < Npad) {
-      uint32_t r[16];
-      tmem_ld16(taddr + 16 * c, r);
-      wait_ld();
-      if (16 * c + 16 <= N) {
+__device__ __forceinline__ void act16(float (&v)[16]) {
+  if (ACT == BBMPC_ACT_TANH) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = act_fast_t<ACT>(__uint_as_float(r[j]));
-      } else {
+    for (int j = 0; j < 16; j += 2) tanh_pair_prescaled(v[j], v[j + 1]);
+  } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int f = 16 * c + j;
-          v[j] = f < N ? act_fast_t<ACT>(__uint_as_float(r[j])) : (f < N + BIAS_COLS ? 1.0f : 0.0f);
-        }
-      }
-    } else {  // pure padding chunk of the next layer's K axis: ones-columns / zeros
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int f = 16 * c + j;
-        v[j] = (f >= N && f < N + BIAS_COLS) ? 1.0f : 0.0f;
-      }
-    }
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-    tmem_st8(taddr + 16 * c, hi);
-    if (passes == 3) tmem_st8(taddr + 16 * c + 8, lo);
-    wait_st();
-    fence_before_sync();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_achunk + 8 * c);
+    for (int j = 0; j < 16; ++j) v[j] = act_fast_t<ACT>(v[j]);
   }
 }
 
-template <int DS_T, int DU_T>
-__global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParams p) {
+// Converts one 16-column accumulator chunk (already in registers) into the bf16 hi/lo A-operand chunk
+// of the next layer and stores it in place.  Full chunks (all 16 columns are real features) take the
+// lean path; the one chunk per layer that holds the ones-columns / padding takes convert_edge, kept
+// out of line so that its column tests are not if-converted into the hot path.
+__device__ __forceinline__ void store_split(uint32_t taddr, int c, const float (&v)[16], int passes) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split_bf16x2_veltkamp(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+  tmem_st8(taddr + 16 * c, hi);
+  if (passes == 3) tmem_st8(taddr + 16 * c + 8, lo);
+}
+template <int ACT>
+__device__ __forceinline__ void convert_full(uint32_t taddr, int c, int passes) {
+  uint32_t r[16];
+  tmem_ld16(taddr + 16 * c, r);
+  wait_ld();
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  act16<ACT>(v);
+  store_split(taddr, c, v, passes);
+}
+template <int ACT>
+__device__ __noinline__ void convert_edge(uint32_t taddr, int c, int Npad, int N, int passes) {
+  float v[16];
+  if (16 * c < Npad) {
+    uint32_t r[16];
+    tmem_ld16(taddr + 16 * c, r);
+    wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+    act16<ACT>(v);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int f = 16 * c + j;
+    if (f >= N || 16 * c >= Npad) v[j] = (f >= N && f < N + BIAS_COLS) ? 1.0f : 0.0f;
+  }
+  store_split(taddr, c, v, passes);
+}
+
+// One hidden-layer epilogue of one warp: 16-column chunks c = sub, sub+EPI_SUB, ... of its TMEM
+// lanes: accumulator -> activation -> bf16 hi/lo -> written back over the same columns -> one
+// arrival on the mbarrier of the chunk's UNIT (pair of chunks, the MMA issuer's wait granularity).
+template <int ACT, bool TR>
+__device__ __forceinline__ void epi_hidden(uint32_t taddr, int Npad, int N, int n_a_chunks, int cb, int ce, int sub,
+                                           int passes, uint32_t bar_unit, int lane, Tracer<TR>& tr) {
+  const int n_full = N >> 4;   // chunks whose 16 columns are all real features
+  for (int c = cb + ((sub - cb) & (EPI_SUB - 1)); c < ce; c += EPI_SUB) {   // chunks of [cb, ce) with c % EPI_SUB == sub
+    tr.rec(0x100u | c);
+    if (c < n_full) convert_full<ACT>(taddr, c, passes);
+    else convert_edge<ACT>(taddr, c, Npad, N, passes);
+    tr.rec(0x300u | c);
+    wait_st();
+    fence_before_sync();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(bar_unit + 8 * (c >> 1));
+      if ((c ^ 1) >= n_a_chunks) mbar_arrive(bar_unit + 8 * (c >> 1));   // lone last chunk stands for its missing partner
+    }
+    tr.rec(0x500u | c);
+  }
+}
+
+template <int DS_T, int DU_T, bool TR, int ACT_T>
+__global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParams p_in) {
+  const TcParams& p = p_in;
+  // watchdog records only exist in the debug/trace build (keeps the production kernel's code small)
+  volatile uint32_t* const dbgp = TR ? p_in.dbg : nullptr;
   extern __shared__ __align__(128) uint8_t smem[];
   const TcSmemLayout lay = tc_layout(p.stage_bytes, p.n_stages, p.mlp.chunks_per_step, p.mlp.jobs_per_step);
   const uint32_t smem_base = smem_u32(smem);
@@ -124,16 +207,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
   // and an mbarrier must never complete two phases ahead of its waiter (parity aliasing).
   const uint32_t bar_achunk = bar_empty + TC_MAX_STAGES * 8;
   const uint32_t bar_x = bar_achunk + 2 * TC_MAX_CHUNKS * 8;  // epilogue -> MMA: layer-0 input of this step written
-  const uint32_t bar_d0 = bar_x + 8;                          // MMA -> epilogue: first-layer accumulator complete
-  const uint32_t bar_d = bar_d0 + 8;                          // MMA -> epilogue: accumulator of a layer l >= 1 complete
-  const uint32_t bar_dout = bar_d + 8;                        // MMA -> epilogue: output accumulator complete
+  // MMA -> conversion warps: accumulator column half h of a first layer (bar_d0 + 8h) / of a later hidden
+  // layer (bar_d + 8h) complete.  One barrier per (kind, half): each is at most one phase ahead of its waiters.
+  const uint32_t bar_d0 = bar_x + 8;
+  const uint32_t bar_d = bar_d0 + 16;
+  const uint32_t bar_dout = bar_d + 16;                       // MMA -> state warps: output accumulator complete
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + lay.tmem_slot);
   float* st_mean_s = reinterpret_cast<float*>(smem + lay.stats);
-  float* st_den_s = st_mean_s + MAX_DS;
-  float* st_mean_t = st_den_s + MAX_DS;
+  float* st_rden_s = st_mean_s + MAX_DS;   // 1 / (std_s + 1e-7)
+  float* st_mean_t = st_rden_s + MAX_DS;
   float* st_den_t = st_mean_t + MAX_DS;
   float* st_mean_a = st_den_t + MAX_DS;
-  float* st_den_a = st_mean_a + MAX_DU;
+  float* st_rden_a = st_mean_a + MAX_DU;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const MlpDev& M = p.mlp;
@@ -149,23 +234,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
   for (int i = tid; i < MAX_DS; i += TC_THREADS) {
     const bool in = norm_on && i < p.dS;
     st_mean_s[i] = in ? p.norm.mean_s[i] : 0.0f;
-    st_den_s[i] = in ? p.norm.den_s[i] : 1.0f;
+    st_rden_s[i] = in ? __frcp_rn(p.norm.den_s[i]) : 1.0f;
     st_mean_t[i] = in ? p.norm.mean_t[i] : 0.0f;
     st_den_t[i] = in ? p.norm.den_t[i] : 1.0f;
   }
   for (int i = tid; i < MAX_DU; i += TC_THREADS) {
     const bool in = norm_on && i < p.dU;
     st_mean_a[i] = in ? p.norm.mean_a[i] : 0.0f;
-    st_den_a[i] = in ? p.norm.den_a[i] : 1.0f;
+    st_rden_a[i] = in ? __frcp_rn(p.norm.den_a[i]) : 1.0f;
   }
   if (tid == 0) {
     for (int s = 0; s < p.n_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int c = 0; c < 2 * TC_MAX_CHUNKS; ++c) mbar_init(bar_achunk + 8 * c, EPI_WARPS / 2);
-    mbar_init(bar_x, EPI_WARPS);
-    mbar_init(bar_d0, 1);
-    mbar_init(bar_d, 1);
+    for (int c = 0; c < 2 * TC_MAX_CHUNKS; ++c) mbar_init(bar_achunk + 8 * c, 8);   // 2 chunks x 4 lane quarters per unit
+    mbar_init(bar_x, 4);
+    mbar_init(bar_d0, 1); mbar_init(bar_d0 + 8, 1);
+    mbar_init(bar_d, 1); mbar_init(bar_d + 8, 1);
     mbar_init(bar_dout, 1);
     fence_mbar_init();
+    // what the conversion warps need to know about hidden layer l, in shared memory (LDS instead of
+    // dynamically indexed kernel-parameter loads in their per-layer prologue)
+    int* cv = reinterpret_cast<int*>(smem + lay.conv);
+    for (int l = 0; l + 1 < nL; ++l) {
+      cv[8 * l + 0] = M.layer[l].Npad; cv[8 * l + 1] = M.layer[l].N; cv[8 * l + 2] = M.layer[l].act;
+      cv[8 * l + 3] = M.layer[l + 1].Kpad >> 4;                  // A-operand chunks of the next layer
+      cv[8 * l + 4] = M.layer[l].nsplit >> 4;                    // first chunk of column half 1 (0: not split)
+    }
   }
   if (warp == 2) {
     tmem_alloc(smem_base + lay.tmem_slot, 512);
@@ -178,92 +271,125 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
 
   const int my_tiles = (p.n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
+  if (warp < 4) {
   if (warp == 0) {
     // ============================================================ producer
+    // One bulk copy per chunk GROUP (up to ~52 KB of consecutive K-chunks of one layer).
     if (lane == 0) {
       const long long total = static_cast<long long>(my_tiles) * p.H * M.chunks_per_step;
       int stage = 0, ci = 0;
       uint32_t phase = 0;
       for (long long i = 0; i < total; ++i) {
         const uint2 e = table[ci];
-        mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.dbg, 0x6000000u | static_cast<uint32_t>(i));
-        mbar_arrive_expect_tx(bar_full + 8 * stage, e.y);
-        bulk_g2s(smem_base + lay.stages + stage * p.stage_bytes, M.wimg + e.x, e.y, bar_full + 8 * stage);
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1, dbgp, 0x6000000u | static_cast<uint32_t>(i));
+        if (p.xflags & 1) { mbar_arrive(bar_full + 8 * stage); }
+        else {
+          mbar_arrive_expect_tx(bar_full + 8 * stage, e.y);
+          bulk_g2s(smem_base + lay.stages + stage * p.stage_bytes, M.wimg + e.x, e.y, bar_full + 8 * stage);
+        }
         if (++ci == M.chunks_per_step) ci = 0;
         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer
-    // The whole warp runs the (warp-uniform) control flow and the barrier waits; one elected lane
-    // issues the tcgen05 instructions.  Per K-chunk the issue path is a handful of integer ops:
-    // everything layer-specific comes pre-digested from the job table.
+    // The whole warp runs the (warp-uniform) control flow; one elected lane issues the tcgen05
+    // instructions.  A successful mbarrier wait costs ~150 cycles of latency in this serial
+    // instruction stream (measured, tools/probe/issue_cost.cu), a K-chunk is only 312 cycles of
+    // tensor work: so weights arrive in multi-chunk groups (one full/empty handshake and one
+    // commit per group), and the state of the NEXT chunk's barrier is probed (non-blocking
+    // test_wait) before the current chunk's MMAs are issued, which hides the probe latency.
     const TcJob* jobs = reinterpret_cast<const TcJob*>(smem + lay.jobs);
     const int n_jobs = M.jobs_per_step;
     const bool three = (p.passes == 3);
     uint32_t stage = 0, phase = 0, px = 0, cph0 = 0, cph1 = 0, rj = 0;  // rj: hidden rounds consumed so far
     const uint32_t stages16 = (smem_base + lay.stages) >> 4, stage16 = static_cast<uint32_t>(p.stage_bytes) >> 4;
     constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1, no swizzle
+    Tracer<TR> tr{p.trace ? p.trace + warp * 1024 : nullptr, 0u, false};
     for (int tile = 0; tile < my_tiles; ++tile) {
       for (int t = 0; t < p.H; ++t) {
+        tr.arm(p.trace && blockIdx.x == 0 && lane == 0 && tile == 0 && t == 1);
         for (int j = 0; j < n_jobs; ++j) {
           const TcJob job = jobs[j];
           const uint32_t d = tmem_base + job.d_col, a = tmem_base + job.a_col;
           const bool from_epi = (job.flags & TCJ_FROM_EPI) != 0;
-          if (job.flags & TCJ_WAIT_X) { mbar_wait(bar_x, px, p.dbg, 0x1000000u); px ^= 1; }
+          if (job.flags & TCJ_WAIT_X) { mbar_wait(bar_x, px, dbgp, 0x1000000u); px ^= 1; }
           const uint32_t set = rj & 1u;
           const uint32_t cph = set ? cph1 : cph0;
           const uint32_t bar_c = bar_achunk + 8 * set * TC_MAX_CHUNKS;
           uint32_t acc = (job.flags & TCJ_ACC_FIRST) ? 1u : 0u;
-          for (uint32_t c = 0; c < job.nchunks; ++c) {
-            if (from_epi) mbar_wait(bar_c + 8 * c, (cph >> c) & 1u, p.dbg, 0x2000000u | (j << 8) | c);
-            mbar_wait(bar_full + 8 * stage, phase, p.dbg, 0x3000000u | (j << 8) | c);
-            fence_after_sync();
-            if (elect_one()) {
-              const uint32_t lo = job.desc_lo_base | ((stages16 + stage * stage16) & 0x3FFFu);
-              const uint64_t bhi = (static_cast<uint64_t>(DESC_HI) << 32) | lo;
-              mma_ts(d, a + 16 * c, bhi, job.idesc, acc);
-              if (three) {
-                mma_ts(d, a + 16 * c + 8, bhi, job.idesc, 1u);
-                mma_ts(d, a + 16 * c, bhi + job.lo_off16, job.idesc, 1u);
+          uint32_t u = 0, pre_ok = 0;
+          const uint32_t n_units = (job.nchunks + 1u) >> 1;
+          for (uint32_t g = 0; g < job.ngroups; ++g) {
+            const uint32_t n = (job.gsz >> (4 * g)) & 15u;
+            mbar_wait(bar_full + 8 * stage, phase, dbgp, 0x3000000u | (j << 8) | g);
+            const uint32_t sbase = (stages16 + stage * stage16);
+            for (uint32_t k = 0; k < n; ++k, ++u) {
+              if (from_epi) {
+                if (!pre_ok) mbar_wait(bar_c + 8 * u, (cph >> u) & 1u, dbgp, 0x2000000u | (j << 8) | u);
+                pre_ok = (u + 1 < n_units) ? mbar_test_wait(bar_c + 8 * (u + 1), (cph >> (u + 1)) & 1u) : 0u;
               }
-              mma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
+              fence_after_sync();
+              tr.rec(0x1000u | (j << 4) | u);
+              const bool two = 2 * u + 1 < job.nchunks;
+              if (elect_one()) {
+                const uint32_t lo = job.desc_lo_base | ((sbase + 2 * k * job.chunk16) & 0x3FFFu);
+                const uint64_t b0 = (static_cast<uint64_t>(DESC_HI) << 32) | lo;
+                const uint32_t a0 = a + 32 * u;
+                mma_ts(d, a0, b0, job.idesc, acc);
+                if (three) {
+                  mma_ts(d, a0 + 8, b0, job.idesc, 1u);
+                  mma_ts(d, a0, b0 + job.lo_off16, job.idesc, 1u);
+                }
+                if (two) {
+                  const uint64_t b1 = b0 + job.chunk16;
+                  mma_ts(d, a0 + 16, b1, job.idesc, 1u);
+                  if (three) {
+                    mma_ts(d, a0 + 24, b1, job.idesc, 1u);
+                    mma_ts(d, a0 + 16, b1 + job.lo_off16, job.idesc, 1u);
+                  }
+                }
+              }
+              __syncwarp();
+              acc = 1u;
             }
+            if (elect_one()) mma_commit(bar_empty + 8 * stage);  // frees the ring stage when these MMAs retire
             __syncwarp();
-            acc = 1u;
             if (++stage == static_cast<uint32_t>(p.n_stages)) { stage = 0; phase ^= 1; }
           }
-          if (from_epi) {
-            const uint32_t used = (1u << job.nchunks) - 1u;
+          if (job.flags & TCJ_ROUND_END) {
+            const uint32_t used = (1u << n_units) - 1u;
             if (set) cph1 ^= used; else cph0 ^= used;
             ++rj;
           }
-          const uint32_t commit = job.flags & TCJ_COMMIT_MASK;
-          if (commit && elect_one())
-            mma_commit(commit == TCJ_COMMIT_D0 ? bar_d0 : (commit == TCJ_COMMIT_D ? bar_d : bar_dout));
+          const uint32_t commit = (job.flags & TCJ_COMMIT_MASK) >> 4;   // 1..4: bar_d0 + 8*(commit-1) (bar_d follows bar_d0)
+          if (commit && elect_one()) mma_commit(commit == 5u ? bar_dout : bar_d0 + 8 * (commit - 1u));
           __syncwarp();
         }
       }
     }
-  } else {
-    // ============================================================ epilogue warps
-    const int e = warp - 2;                 // 0..7
-    const int q = warp & 3;                 // TMEM lane quarter this warp may touch
-    const int half = e >> 2;                // which interleaved half of the 16-column chunks
-    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tm = tmem_base + lane_base;
+  }
+  } else if (warp < 8) {
+    // ============================================================ state warps (one per TMEM lane quarter)
+    // Own the trajectory state, action and return of their 32 rows in registers for all H steps:
+    // build the layer-0 input (process_input), consume the output accumulator (process_output,
+    // reward, NaN guard).  They sleep on bar_dout while the hidden layers run.
+    const int q = warp & 3;
+    const uint32_t tm = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int row_in_tile = q * 32 + lane;
-    uint32_t pd0 = 0, pd = 0, pdout = 0, rj = 0;  // rj: hidden rounds produced so far (chunk-barrier set = rj & 1)
+    uint32_t pdout = 0;
     const int kp0_chunks = M.layer[0].Kpad >> 4;
-    const float n_members_f = static_cast<float>(nM);
+    const float inv_members = __frcp_rn(static_cast<float>(nM));
+    Tracer<TR> tr{p.trace ? p.trace + warp * 1024 : nullptr, 0u, false};
 
     for (int tile = 0; tile < my_tiles; ++tile) {
       const int row = (static_cast<int>(blockIdx.x) + tile * static_cast<int>(gridDim.x)) * TILE_ROWS + row_in_tile;
       const bool valid = row < p.rows;
       const int arow = valid ? row : 0;
       float s[DS_T];
+      const float* srow_ptr = p.states + static_cast<size_t>(arow % p.A) * p.dS;
 #pragma unroll
-      for (int i = 0; i < DS_T; ++i) s[i] = (i < p.dS) ? p.states[(arow % p.A) * p.dS + i] : 0.0f;
+      for (int i = 0; i < DS_T; ++i) s[i] = (i < p.dS) ? srow_ptr[i] : 0.0f;
       float ret = 0.0f;
       const float* arow_ptr = p.actions + static_cast<size_t>(arow) * p.H * p.dU;
       float a_next[DU_T];
@@ -271,6 +397,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
       for (int i = 0; i < DU_T; ++i) a_next[i] = (i < p.dU && p.H > 0) ? arow_ptr[i] : 0.0f;
 
       for (int t = 0; t < p.H; ++t) {
+        tr.arm(p.trace && blockIdx.x == 0 && lane == 0 && tile == 0 && t == 1);
+        tr.rec(0x10u);
         float a[DU_T];
 #pragma unroll
         for (int i = 0; i < DU_T; ++i) a[i] = a_next[i];
@@ -282,19 +410,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
         constexpr int KP0_T = (DU_T + DS_T + BIAS_COLS + 15) / 16;
 #pragma unroll
         for (int c = 0; c < KP0_T; ++c) {
-          if (c < kp0_chunks && (c & 1) == half) {
+          if (c < kp0_chunks) {
             float x[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int k = 16 * c + j;
               float v;
               if (k < DU_T) {
-                v = (k < p.dU) ? __fdiv_rn(__fsub_rn(a[k < DU_T ? k : 0], st_mean_a[k < DU_T ? k : 0]), st_den_a[k < DU_T ? k : 0]) : 0.0f;
+                v = (k < p.dU) ? __fmul_rn(__fsub_rn(a[k < DU_T ? k : 0], st_mean_a[k < DU_T ? k : 0]), st_rden_a[k < DU_T ? k : 0]) : 0.0f;
               } else {
                 const int i = k - DU_T;
                 const float one_or_zero = (i >= p.dS && i < p.dS + BIAS_COLS) ? 1.0f : 0.0f;
                 if (i < DS_T)
-                  v = (i < p.dS) ? __fdiv_rn(__fsub_rn(s[i < DS_T ? i : 0], st_mean_s[i < DS_T ? i : 0]), st_den_s[i < DS_T ? i : 0]) : one_or_zero;
+                  v = (i < p.dS) ? __fmul_rn(__fsub_rn(s[i < DS_T ? i : 0], st_mean_s[i < DS_T ? i : 0]), st_rden_s[i < DS_T ? i : 0]) : one_or_zero;
                 else
                   v = one_or_zero;
               }
@@ -307,51 +435,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
             if (p.passes == 3) tmem_st8(tm + p.col_x + 16 * c + 8, lo);
           }
         }
+        tr.rec(0x13u);
         wait_st();
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_x);
-
-        // ---- hidden layers of every member: accumulator -> activation -> next A operand, in place
-        int idx = 0;
-        for (int mm = 0; mm < nM; ++mm) {
-          for (int l = 0; l + 1 < nL; ++l, ++idx) {
-            const LayerDev& L = M.layer[l];
-            const int n_a_chunks = M.layer[l + 1].Kpad >> 4;
-            const uint32_t taddr = tm + ((idx & 1) ? p.col_buf1 : p.col_buf0);
-            if (l == 0) { mbar_wait(bar_d0, pd0, p.dbg, 0x4000000u | (mm << 16)); pd0 ^= 1; }
-            else { mbar_wait(bar_d, pd, p.dbg, 0x4000000u | (mm << 16) | (l << 8)); pd ^= 1; }
-            fence_after_sync();
-            const uint32_t bar_set = bar_achunk + 8 * ((rj & 1u) * TC_MAX_CHUNKS);
-            ++rj;
-            switch (L.act) {
-              case BBMPC_ACT_TANH: epi_hidden<BBMPC_ACT_TANH>(taddr, L.Npad, L.N, n_a_chunks, half, p.passes, bar_set, lane); break;
-              case BBMPC_ACT_RELU: epi_hidden<BBMPC_ACT_RELU>(taddr, L.Npad, L.N, n_a_chunks, half, p.passes, bar_set, lane); break;
-              case BBMPC_ACT_SIGMOID: epi_hidden<BBMPC_ACT_SIGMOID>(taddr, L.Npad, L.N, n_a_chunks, half, p.passes, bar_set, lane); break;
-              default: epi_hidden<BBMPC_ACT_NONE>(taddr, L.Npad, L.N, n_a_chunks, half, p.passes, bar_set, lane); break;
-            }
-          }
-        }
+        tr.rec(0x11u);
 
         // ---- output layer (sum over members) -> process_output -> reward
-        mbar_wait(bar_dout, pdout, p.dbg, 0x5000000u); pdout ^= 1;
+        mbar_wait(bar_dout, pdout, dbgp, 0x5000000u); pdout ^= 1;
         fence_after_sync();
+        tr.rec(0x30u);
         float s2[DS_T];
         {
           const LayerDev& Lo = M.layer[nL - 1];
+          uint32_t r[DS_T / 8][8];
 #pragma unroll
-          for (int c = 0; c < DS_T / 8; ++c) {
-            uint32_t r[8];
-            tmem_ld8(tm + p.col_dout + 8 * c, r);
-            wait_ld();
+          for (int c = 0; c < DS_T / 8; ++c) tmem_ld8(tm + p.col_dout + 8 * c, r[c]);
+          wait_ld();
+          tr.rec(0x32u);
+          if (nM == 1 && Lo.act != BBMPC_ACT_NONE) {   // non-linear output layer (single model only): rare, kept out of line
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int i = 8 * c + j;
-              float y = act_fast(__uint_as_float(r[j]), nM == 1 ? Lo.act : BBMPC_ACT_NONE);
-              if (nM > 1) y = __fdiv_rn(y, n_members_f);
-              const float dlt = norm_on ? __fadd_rn(st_mean_t[i], __fmul_rn(y, st_den_t[i])) : y;
-              s2[i] = (i < p.dS) ? __fadd_rn(dlt, s[i]) : 0.0f;
-            }
+            for (int c = 0; c < DS_T / 8; ++c)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r[c][j] = __float_as_uint(act_fast(__uint_as_float(r[c][j]), Lo.act));
+          }
+#pragma unroll
+          for (int i = 0; i < DS_T; ++i) {
+            float y = __uint_as_float(r[i / 8][i % 8]);
+            if (nM > 1) y = __fmul_rn(y, inv_members);
+            const float dlt = norm_on ? __fadd_rn(st_mean_t[i], __fmul_rn(y, st_den_t[i])) : y;
+            s2[i] = (i < p.dS) ? __fadd_rn(dlt, s[i]) : 0.0f;
           }
         }
         // all of this thread's TMEM reads of D_out are complete (wait_ld) before the next arrive.
@@ -384,11 +498,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
         ret = __fadd_rn(ret, r_t);
 #pragma unroll
         for (int i = 0; i < DS_T; ++i) s[i] = s2[i];
+        tr.rec(0x31u);
       }
-      if (half == 0 && valid) {
+      if (valid) {
         float r = isnan(ret) ? -1e6f : ret;  // deterministic.py:75-77
         if (p.penalty) r = __fsub_rn(r, p.penalty[row]);
         p.returns[row] = r;
+      }
+    }
+  } else {
+    // ============================================================ conversion warps
+    // EPI_SUB warps per TMEM lane quarter turn hidden-layer accumulators into the next layer's A operand.
+    const int e = warp - 8;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may touch (hardware: warp id % 4)
+    const int sub = e >> 2;                 // 0 .. EPI_SUB-1
+    const uint32_t tm = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t pd = 0, rj = 0;  // pd: phase bits of the four accumulator barriers; rj: hidden rounds produced so far
+    const int* cv = reinterpret_cast<const int*>(smem + lay.conv);
+    Tracer<TR> tr{p.trace ? p.trace + warp * 1024 : nullptr, 0u, false};
+    const long long n_steps = static_cast<long long>(my_tiles) * p.H;
+    for (long long st = 0; st < n_steps; ++st) {
+      tr.arm(p.trace && blockIdx.x == 0 && lane == 0 && st == 1);
+      int idx = 0;
+      for (int mm = 0; mm < nM; ++mm) {
+        for (int l = 0; l + 1 < nL; ++l, ++idx) {
+          const int Npad = cv[8 * l], N = cv[8 * l + 1], act = (p.xflags & 2) ? BBMPC_ACT_NONE : cv[8 * l + 2];
+          const int n_a_chunks = cv[8 * l + 3], csplit = cv[8 * l + 4];
+          const uint32_t taddr = tm + ((idx & 1) ? p.col_buf1 : p.col_buf0);
+          const uint32_t bar_set = bar_achunk + 8 * ((rj & 1u) * TC_MAX_CHUNKS);
+          ++rj;
+          for (int h = 0; h < (csplit ? 2 : 1); ++h) {
+            const uint32_t kind = (l == 0 ? 0u : 2u) + h;
+            mbar_wait(bar_d0 + 8 * kind, (pd >> kind) & 1u, dbgp, 0x4000000u | (mm << 16) | (l << 8) | h);
+            pd ^= 1u << kind;
+            fence_after_sync();
+            tr.rec(0x20u | (mm << 12) | (l << 8) | (h << 6));
+            const int cb = h ? csplit : 0, ce = (csplit && !h) ? csplit : n_a_chunks;
+            if (ACT_T >= 0) {
+              epi_hidden<(ACT_T >= 0 ? ACT_T : 0), TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tr);
+            } else {
+              switch (act) {
+                case BBMPC_ACT_TANH: epi_hidden<BBMPC_ACT_TANH, TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tr); break;
+                case BBMPC_ACT_RELU: epi_hidden<BBMPC_ACT_RELU, TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tr); break;
+                case BBMPC_ACT_SIGMOID: epi_hidden<BBMPC_ACT_SIGMOID, TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tr); break;
+                default: epi_hidden<BBMPC_ACT_NONE, TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tr); break;
+              }
+            }
+          }
+        }
       }
     }
   }
@@ -402,16 +559,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
 // ---------------------------------------------------------------------------- host launcher
 template <int DS_T, int DU_T>
 static int launch_t(bbmpc_ctx* ctx, const TcParams& p, int grid, size_t smem_bytes, cudaStream_t st) {
-  BB_CUDA(ctx, cudaFuncSetAttribute(rollout_tc_kernel<DS_T, DU_T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(smem_bytes)));
-  rollout_tc_kernel<DS_T, DU_T><<<grid, TC_THREADS, smem_bytes, st>>>(p);
+  // all hidden layers tanh (every reference tutorial): specialised kernel without the per-layer switch
+  bool all_tanh = !(p.xflags & 2);
+  for (int l = 0; l + 1 < p.mlp.n_layers; ++l) all_tanh = all_tanh && p.mlp.layer[l].act == BBMPC_ACT_TANH;
+  auto kern = (p.trace || p.dbg) ? rollout_tc_kernel<DS_T, DU_T, true, -1>
+                                 : (all_tanh ? rollout_tc_kernel<DS_T, DU_T, false, BBMPC_ACT_TANH> : rollout_tc_kernel<DS_T, DU_T, false, -1>);
+  BB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+  kern<<<grid, TC_THREADS, smem_bytes, st>>>(p);
   BB_LAUNCH_CHECK(ctx);
+  if (p.trace) {
+    cudaStreamSynchronize(st);
+    static std::vector<uint32_t> h(32 * 1024);
+    cudaMemcpy(h.data(), p.trace, h.size() * 4, cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(getenv("BBMPC_TC_TRACE"), "w")) {
+      for (int w = 0; w < TC_WARPS; ++w)
+        for (int i = 0; i < 500; ++i)
+          if (h[w * 1024 + 2 * i]) fprintf(f, "%d %x %u\n", w, h[w * 1024 + 2 * i], h[w * 1024 + 2 * i + 1]);
+      fclose(f);
+    }
+    cudaMemset(p.trace, 0, h.size() * 4);
+  }
   if (p.dbg) {  // BBMPC_DEBUG=1: synchronise and dump the watchdog record of a starved pipeline
     const cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
       uint32_t* h = static_cast<uint32_t*>(ctx->dbg_host);
       for (int b = 0; b < 2; ++b)
-        for (int w = 0; w < 10; ++w) {
+        for (int w = 0; w < TC_WARPS; ++w) {
           const uint32_t* r = h + 128 * b + 8 * w;
           if (r[0]) fprintf(stderr, "[bbmpc watchdog] blk%%2=%d warp=%d tid=%u bar=+%u parity=%u tag=%08x\n", b, w, r[0] & 0xFFFF,
                             r[1], r[2], r[3]);
@@ -450,15 +623,18 @@ int launch_rollout_tc(bbmpc_ctx* ctx, const float* states, const float* actions,
   p.states = states; p.actions = actions; p.returns = returns; p.penalty = penalty;
   p.rows = rows; p.A = A; p.H = H; p.passes = passes;
   p.n_tiles = (rows + TILE_ROWS - 1) / TILE_ROWS;
-  const int nL = m.mlp.n_layers;
-  int stage = 0;
-  for (int l = 0; l < nL; ++l)
-    if (m.mlp.layer[l].chunk_bytes > stage) stage = m.mlp.layer[l].chunk_bytes;
+  const int stage = m.mlp.stage_bytes;
   int buf_w = 0;
   if (!tc_column_map(m.mlp, &buf_w, &p.col_x, &p.col_dout))
     return fail(ctx, BBMPC_EINVAL, "tensor-core path: TMEM column budget exceeded");
   p.col_buf0 = 0;
   p.col_buf1 = 256;
+  if (const char* x = getenv("BBMPC_TC_X")) p.xflags = atoi(x);
+  if (getenv("BBMPC_TC_TRACE")) {
+    static uint32_t* tbuf = nullptr;
+    if (!tbuf) { BB_CUDA(ctx, cudaMalloc(&tbuf, 32 * 1024 * 4)); BB_CUDA(ctx, cudaMemset(tbuf, 0, 32 * 1024 * 4)); }
+    p.trace = tbuf;
+  }
   if (getenv("BBMPC_DEBUG")) {
     if (!ctx->dbg_host) {
       BB_CUDA(ctx, cudaHostAlloc(&ctx->dbg_host, 1024, cudaHostAllocMapped));

@@ -206,4 +206,15 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
   lo = pack_bf16x2(a - bf16_lo_as_f32(hi), b - bf16_hi_as_f32(hi));
 }
 
+// Same split with the bf16 rounding of `hi` done on the FMA pipe (Veltkamp: c = (2^16+1) x,
+// hi = c - (c - x) is x rounded to 8 significant bits, exactly a bf16), so that only the `lo` pair
+// needs a cvt (which shares the MUFU pipe).  Requires |x| < 2^111 (no overflow of c); used for
+// activations and normalised inputs.
+__device__ __forceinline__ void split_bf16x2_veltkamp(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const float ca = __fmul_rn(a, 65537.0f), cb = __fmul_rn(b, 65537.0f);
+  const float ha = __fsub_rn(ca, __fsub_rn(ca, a)), hb = __fsub_rn(cb, __fsub_rn(cb, b));
+  asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(hi) : "r"(__float_as_uint(ha)), "r"(__float_as_uint(hb)));
+  lo = pack_bf16x2(__fsub_rn(a, ha), __fsub_rn(b, hb));
+}
+
 }  // namespace tc05
