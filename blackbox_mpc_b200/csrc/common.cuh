@@ -51,7 +51,7 @@ struct TcJob {
   uint32_t gsz;            // ... of gsz[4*g +: 4] UNITS (pairs of K-chunks) each: one bulk copy, one full/empty barrier pair per group
   uint32_t pad[2];
 };
-constexpr int TC_GROUP_CAP_BYTES = 53248;  // ring-stage capacity target (4 K-chunks of a 208-wide layer)
+constexpr int TC_GROUP_CAP_BYTES = 27648;  // ring-stage capacity target (one unit = 2 K-chunks of a 208-wide layer)
 constexpr int TC_MAX_GROUPS = 8;
 enum : uint32_t {
   TCJ_WAIT_X = 1u,        // first job of a step: wait until the epilogue has written the layer-0 input
@@ -75,6 +75,10 @@ struct MlpDev {
   int early_l0;    // chunk-table order: first layer of member m+1 issued ahead of the output layer of member m
   const TcJob* jobs;   // [jobs_per_step]
   int jobs_per_step;
+  // "solo" tables: the jobs / chunk groups of ONE member (member 0's image offsets; no early first-layer
+  // issue, output layer not accumulated) — used when the members of an ensemble run on different CTAs.
+  const uint2* solo_table; int solo_groups_per_step;
+  const TcJob* solo_jobs; int solo_jobs_per_step;
   int max_width;   // widest activation (incl. input) — SIMT smem sizing
 };
 
@@ -88,6 +92,8 @@ struct ModelHost {
   uint8_t* wimg_buf = nullptr;
   uint2* chunk_table_buf = nullptr;
   TcJob* jobs_buf = nullptr;
+  uint2* solo_table_buf = nullptr;
+  TcJob* solo_jobs_buf = nullptr;
   float* norm_buf = nullptr;
   bool tc_ok = false;
   std::string tc_why;  // why the tensor-core path is unavailable for this model
@@ -107,6 +113,9 @@ struct bbmpc_ctx {
   // few-row step kernel (optimizer tail): per-member partial outputs + arrival counters
   float* step_scratch = nullptr;
   unsigned* step_counters = nullptr;
+  // member-parallel rollout: per-group exchange of the members' raw outputs + arrival counters
+  float* tc_xchg = nullptr; size_t tc_xchg_floats = 0;
+  unsigned* tc_flags = nullptr; int tc_flags_n = 0;
   void* dbg_host = nullptr;  // BBMPC_DEBUG=1: host-mapped watchdog record of the tensor-core kernel
   // rollout-kernel timing (bbmpc_profile_*): event pairs recorded around every rollout launch
   bool prof_on = false;

@@ -106,6 +106,7 @@ int resolve_precision(const bbmpc_ctx* ctx) {
 
 static void free_model(ModelHost& m) {
   cudaFree(m.w32_buf); cudaFree(m.wimg_buf); cudaFree(m.chunk_table_buf); cudaFree(m.jobs_buf);
+  cudaFree(m.solo_table_buf); cudaFree(m.solo_jobs_buf); m.solo_table_buf = nullptr; m.solo_jobs_buf = nullptr;
   m.w32_buf = nullptr; m.wimg_buf = nullptr; m.chunk_table_buf = nullptr; m.jobs_buf = nullptr;
   m.mlp = MlpDev{};
   m.tc_ok = false;
@@ -185,6 +186,7 @@ void bbmpc_ctx_destroy(bbmpc_ctx* ctx) {
   free_model(ctx->model);
   cudaFree(ctx->model.norm_buf);
   cudaFree(ctx->step_scratch); cudaFree(ctx->step_counters);
+  cudaFree(ctx->tc_xchg); cudaFree(ctx->tc_flags);
   if (ctx->dbg_host) cudaFreeHost(ctx->dbg_host);
   for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
   delete ctx;
@@ -308,6 +310,7 @@ int bbmpc_model_set_mlp(bbmpc_ctx* ctx, int n_members, int n_layers, const int* 
     tc_column_map(p, &buf_w, &col_x, &col_dout);
     int stage_bytes = 0;
     // One job per (member, layer, column half), in MMA issue order.
+    bool solo = false;
     auto push_layer = [&](int mm, int l) {
       const LayerDev& L = p.layer[l];
       const int nch = L.Kpad / 16;
@@ -349,11 +352,11 @@ int bbmpc_model_set_mlp(bbmpc_ctx* ctx, int n_members, int n_layers, const int* 
         j.ngroups = ngroups;
         j.gsz = gsz;
         uint32_t commit;
-        if (last) commit = (mm == n_members - 1) ? TCJ_COMMIT_DOUT : 0u;
+        if (last) commit = (solo || mm == n_members - 1) ? TCJ_COMMIT_DOUT : 0u;
         else if (l == 0) commit = h ? TCJ_COMMIT_D0H1 : TCJ_COMMIT_D0H0;
         else commit = h ? TCJ_COMMIT_DH1 : TCJ_COMMIT_DH0;
         j.flags = (l == 0 && mm == 0 && h == 0 ? TCJ_WAIT_X : 0u) | (l > 0 && h == 0 ? TCJ_FROM_EPI : 0u) |
-                  (l > 0 && h == n_halves - 1 ? TCJ_ROUND_END : 0u) | (last && mm > 0 ? TCJ_ACC_FIRST : 0u) | commit;
+                  (l > 0 && h == n_halves - 1 ? TCJ_ROUND_END : 0u) | (last && mm > 0 && !solo ? TCJ_ACC_FIRST : 0u) | commit;
         jobs.push_back(j);
       }
     };
@@ -370,6 +373,22 @@ int bbmpc_model_set_mlp(bbmpc_ctx* ctx, int n_members, int n_layers, const int* 
         push_layer(mm, n_layers - 1);
       }
     }
+    // solo tables (member 0 only, plain layer order)
+    std::vector<uint2> table_all = table;
+    std::vector<TcJob> jobs_all = jobs;
+    const int stage_all = stage_bytes;
+    table.clear(); jobs.clear(); solo = true;
+    for (int l = 0; l < n_layers; ++l) push_layer(0, l);
+    std::vector<uint2> table_solo = table;
+    std::vector<TcJob> jobs_solo = jobs;
+    table = table_all; jobs = jobs_all;
+    if (stage_all > stage_bytes) stage_bytes = stage_all;
+    BB_CUDA(ctx, cudaMalloc(&m.solo_table_buf, table_solo.size() * sizeof(uint2)));
+    BB_CUDA(ctx, cudaMemcpyAsync(m.solo_table_buf, table_solo.data(), table_solo.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+    BB_CUDA(ctx, cudaMalloc(&m.solo_jobs_buf, jobs_solo.size() * sizeof(TcJob)));
+    BB_CUDA(ctx, cudaMemcpyAsync(m.solo_jobs_buf, jobs_solo.data(), jobs_solo.size() * sizeof(TcJob), cudaMemcpyHostToDevice, st));
+    p.solo_table = m.solo_table_buf; p.solo_groups_per_step = static_cast<int>(table_solo.size());
+    p.solo_jobs = m.solo_jobs_buf; p.solo_jobs_per_step = static_cast<int>(jobs_solo.size());
     BB_CUDA(ctx, cudaMalloc(&m.chunk_table_buf, table.size() * sizeof(uint2)));
     BB_CUDA(ctx, cudaMemcpyAsync(m.chunk_table_buf, table.data(), table.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
     BB_CUDA(ctx, cudaMalloc(&m.jobs_buf, jobs.size() * sizeof(TcJob)));

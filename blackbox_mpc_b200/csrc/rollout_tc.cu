@@ -47,6 +47,7 @@ constexpr int TC_THREADS = 32 * TC_WARPS;
 constexpr int TC_MAX_STAGES = 24;
 constexpr int TC_MAX_CHUNKS = 16;   // K chunks of one layer (Kpad <= 256)
 constexpr int TILE_ROWS = 128;
+constexpr int MAX_DU_T = 16;
 
 struct TcParams {
   MlpDev mlp;
@@ -56,19 +57,27 @@ struct TcParams {
   int rows, A, H, n_tiles, passes;
   int stage_bytes, n_stages;
   int col_buf0, col_buf1, col_x, col_dout;  // TMEM column map
+  // issue tables of this launch (full ensemble per CTA, or one member per CTA)
+  const TcJob* jobs; int n_jobs; const uint2* table; int n_table;
+  // member-parallel mode: the n_members CTAs of a group share a tile; each contracts ONE member and the
+  // members' raw outputs are exchanged through `xchg` (L2) once per horizon step.  0 = one CTA per tile.
+  int group_mode; float* xchg; unsigned* flags;
+  int xs_bytes;   // > 0: the group's outputs are staged in shared memory by bulk copies (else read from L2 directly)
   uint32_t* dbg;  // host-mapped watchdog record (BBMPC_DEBUG=1), else nullptr
   uint32_t* trace; // BBMPC_TC_TRACE: per-warp (tag, clock) records of CTA 0, step 1
   int xflags;     // BBMPC_TC_X timing experiments (results are garbage): 1 = no weight loads, 2 = identity activations
 };
 
 struct TcSmemLayout {
-  uint32_t stages, table, jobs, bars, tmem_slot, stats, conv, total;
+  uint32_t stages, xs, acts, table, jobs, bars, tmem_slot, stats, conv, total;
 };
-constexpr int TC_NUM_BARS = 2 * TC_MAX_STAGES + 2 * TC_MAX_CHUNKS + 6;
-__host__ __device__ inline TcSmemLayout tc_layout(int stage_bytes, int n_stages, int groups_per_step, int jobs_per_step) {
+constexpr int TC_NUM_BARS = 2 * TC_MAX_STAGES + 2 * TC_MAX_CHUNKS + 7;
+__host__ __device__ inline TcSmemLayout tc_layout(int stage_bytes, int n_stages, int groups_per_step, int jobs_per_step, int xs_bytes) {
   TcSmemLayout L;
   uint32_t off = 0;
   L.stages = off; off += static_cast<uint32_t>(stage_bytes) * n_stages;
+  L.xs = off;     off += static_cast<uint32_t>(xs_bytes);   // member-parallel mode: staging of the group's outputs
+  L.acts = off;   off += 2u * TILE_ROWS * MAX_DU_T * 4u;    // next step's actions, prefetched with cp.async (double buffer)
   L.table = off;  off += static_cast<uint32_t>(groups_per_step) * 8;
   off = (off + 15u) & ~15u;
   L.jobs = off;   off += static_cast<uint32_t>(jobs_per_step) * sizeof(TcJob);
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
   // watchdog records only exist in the debug/trace build (keeps the production kernel's code small)
   volatile uint32_t* const dbgp = TR ? p_in.dbg : nullptr;
   extern __shared__ __align__(128) uint8_t smem[];
-  const TcSmemLayout lay = tc_layout(p.stage_bytes, p.n_stages, p.mlp.chunks_per_step, p.mlp.jobs_per_step);
+  const TcSmemLayout lay = tc_layout(p.stage_bytes, p.n_stages, p.n_table, p.n_jobs, p.xs_bytes);
   const uint32_t smem_base = smem_u32(smem);
   const uint2* table = reinterpret_cast<const uint2*>(smem + lay.table);
   const uint32_t bar_full = smem_base + lay.bars;
@@ -212,6 +221,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
   const uint32_t bar_d0 = bar_x + 8;
   const uint32_t bar_d = bar_d0 + 16;
   const uint32_t bar_dout = bar_d + 16;                       // MMA -> state warps: output accumulator complete
+  const uint32_t bar_xs = bar_dout + 8;                       // bulk copies of the group's outputs landed (member-parallel mode)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + lay.tmem_slot);
   float* st_mean_s = reinterpret_cast<float*>(smem + lay.stats);
   float* st_rden_s = st_mean_s + MAX_DS;   // 1 / (std_s + 1e-7)
@@ -227,10 +237,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
   const bool norm_on = p.norm.enabled != 0;
 
   // ---------------------------------------------------------------- one-time setup
-  for (int i = tid; i < M.chunks_per_step; i += TC_THREADS)
-    reinterpret_cast<uint2*>(smem + lay.table)[i] = M.chunk_table[i];
-  for (int i = tid; i < M.jobs_per_step * static_cast<int>(sizeof(TcJob) / 16); i += TC_THREADS)
-    reinterpret_cast<uint4*>(smem + lay.jobs)[i] = reinterpret_cast<const uint4*>(M.jobs)[i];
+  for (int i = tid; i < p.n_table; i += TC_THREADS)
+    reinterpret_cast<uint2*>(smem + lay.table)[i] = p.table[i];
+  for (int i = tid; i < p.n_jobs * static_cast<int>(sizeof(TcJob) / 16); i += TC_THREADS)
+    reinterpret_cast<uint4*>(smem + lay.jobs)[i] = reinterpret_cast<const uint4*>(p.jobs)[i];
   for (int i = tid; i < MAX_DS; i += TC_THREADS) {
     const bool in = norm_on && i < p.dS;
     st_mean_s[i] = in ? p.norm.mean_s[i] : 0.0f;
@@ -250,6 +260,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
     mbar_init(bar_d0, 1); mbar_init(bar_d0 + 8, 1);
     mbar_init(bar_d, 1); mbar_init(bar_d + 8, 1);
     mbar_init(bar_dout, 1);
+    mbar_init(bar_xs, 1);
     fence_mbar_init();
     // what the conversion warps need to know about hidden layer l, in shared memory (LDS instead of
     // dynamically indexed kernel-parameter loads in their per-layer prologue)
@@ -269,14 +280,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int my_tiles = (p.n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  // tile ownership: CTA b owns tiles b, b+grid, ... ; in member-parallel mode the nM consecutive CTAs of
+  // group g = b / nM own tiles g, g+G, ... together and CTA b contracts member b % nM.
+  const int n_owners = p.group_mode ? static_cast<int>(gridDim.x) / nM : static_cast<int>(gridDim.x);
+  const int owner = p.group_mode ? static_cast<int>(blockIdx.x) / nM : static_cast<int>(blockIdx.x);
+  const int my_member = p.group_mode ? static_cast<int>(blockIdx.x) % nM : 0;
+  const int my_tiles = (p.n_tiles - owner + n_owners - 1) / n_owners;
+  const int nM_here = p.group_mode ? 1 : nM;   // members contracted by this CTA
 
   if (warp < 4) {
   if (warp == 0) {
     // ============================================================ producer
     // One bulk copy per chunk GROUP (up to ~52 KB of consecutive K-chunks of one layer).
     if (lane == 0) {
-      const long long total = static_cast<long long>(my_tiles) * p.H * M.chunks_per_step;
+      const long long total = static_cast<long long>(my_tiles) * p.H * p.n_table;
+      const uint8_t* wimg = M.wimg + static_cast<size_t>(my_member) * M.img_member_stride;
       int stage = 0, ci = 0;
       uint32_t phase = 0;
       for (long long i = 0; i < total; ++i) {
@@ -285,9 +303,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
         if (p.xflags & 1) { mbar_arrive(bar_full + 8 * stage); }
         else {
           mbar_arrive_expect_tx(bar_full + 8 * stage, e.y);
-          bulk_g2s(smem_base + lay.stages + stage * p.stage_bytes, M.wimg + e.x, e.y, bar_full + 8 * stage);
+          bulk_g2s(smem_base + lay.stages + stage * p.stage_bytes, wimg + e.x, e.y, bar_full + 8 * stage);
         }
-        if (++ci == M.chunks_per_step) ci = 0;
+        if (++ci == p.n_table) ci = 0;
         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -300,7 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
     // commit per group), and the state of the NEXT chunk's barrier is probed (non-blocking
     // test_wait) before the current chunk's MMAs are issued, which hides the probe latency.
     const TcJob* jobs = reinterpret_cast<const TcJob*>(smem + lay.jobs);
-    const int n_jobs = M.jobs_per_step;
+    const int n_jobs = p.n_jobs;
     const bool three = (p.passes == 3);
     uint32_t stage = 0, phase = 0, px = 0, cph0 = 0, cph1 = 0, rj = 0;  // rj: hidden rounds consumed so far
     const uint32_t stages16 = (smem_base + lay.stages) >> 4, stage16 = static_cast<uint32_t>(p.stage_bytes) >> 4;
@@ -383,7 +401,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
     Tracer<TR> tr{p.trace ? p.trace + warp * 1024 : nullptr, 0u, false};
 
     for (int tile = 0; tile < my_tiles; ++tile) {
-      const int row = (static_cast<int>(blockIdx.x) + tile * static_cast<int>(gridDim.x)) * TILE_ROWS + row_in_tile;
+      const int row = (owner + tile * n_owners) * TILE_ROWS + row_in_tile;
       const bool valid = row < p.rows;
       const int arow = valid ? row : 0;
       float s[DS_T];
@@ -392,20 +410,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
       for (int i = 0; i < DS_T; ++i) s[i] = (i < p.dS) ? srow_ptr[i] : 0.0f;
       float ret = 0.0f;
       const float* arow_ptr = p.actions + static_cast<size_t>(arow) * p.H * p.dU;
-      float a_next[DU_T];
+      // actions reach the thread through shared memory: step t+1's dU floats are fetched with cp.async while
+      // step t runs (a register prefetch gets sunk to its use by the compiler and exposes the L2 latency).
+      float* act_s = reinterpret_cast<float*>(smem + lay.acts) + row_in_tile;   // [buf][i][row]
+      auto fetch_actions = [&](int t_next) {
+        const uint32_t dst = smem_u32(act_s + (t_next & 1) * (MAX_DU_T * TILE_ROWS));
+        const float* src = arow_ptr + static_cast<size_t>(t_next) * p.dU;
 #pragma unroll
-      for (int i = 0; i < DU_T; ++i) a_next[i] = (i < p.dU && p.H > 0) ? arow_ptr[i] : 0.0f;
+        for (int i = 0; i < DU_T; ++i)
+          if (i < p.dU) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + i * TILE_ROWS * 4), "l"(src + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      if (p.H > 0) fetch_actions(0);
 
       for (int t = 0; t < p.H; ++t) {
         tr.arm(p.trace && blockIdx.x == 0 && lane == 0 && tile == 0 && t == 1);
         tr.rec(0x10u);
         float a[DU_T];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < DU_T; ++i) a[i] = a_next[i];
-        if (t + 1 < p.H) {
-#pragma unroll
-          for (int i = 0; i < DU_T; ++i) if (i < p.dU) a_next[i] = arow_ptr[(t + 1) * p.dU + i];
-        }
+        for (int i = 0; i < DU_T; ++i) a[i] = (i < p.dU) ? act_s[(t & 1) * (MAX_DU_T * TILE_ROWS) + i * TILE_ROWS] : 0.0f;
+        if (t + 1 < p.H) fetch_actions(t + 1);
+        tr.rec(0x12u);
         // ---- process_input: X = [norm(a) (DU_T slots) | norm(s) | 1 1 1 | 0...] -> TMEM
         constexpr int KP0_T = (DU_T + DS_T + BIAS_COLS + 15) / 16;
 #pragma unroll
@@ -454,6 +480,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
           for (int c = 0; c < DS_T / 8; ++c) tmem_ld8(tm + p.col_dout + 8 * c, r[c]);
           wait_ld();
           tr.rec(0x32u);
+          if (p.group_mode) {
+            // ---- member-parallel exchange: publish this member's raw output, wait for the whole group,
+            // sum the members in member order (identical on every CTA of the group).
+            const long long gstep = static_cast<long long>(tile) * p.H + t;
+            const int par = static_cast<int>(gstep & 1);
+            float* base = p.xchg + (static_cast<size_t>(owner) * 2 + par) * nM * (DS_T * TILE_ROWS);
+            float4* mine = reinterpret_cast<float4*>(base + (static_cast<size_t>(my_member) * TILE_ROWS + row_in_tile) * DS_T);
+#pragma unroll
+            for (int c = 0; c < DS_T / 4; ++c)
+              __stcg(mine + c, make_float4(__uint_as_float(r[c / 2][4 * (c & 1)]), __uint_as_float(r[c / 2][4 * (c & 1) + 1]),
+                                           __uint_as_float(r[c / 2][4 * (c & 1) + 2]), __uint_as_float(r[c / 2][4 * (c & 1) + 3])));
+            tr.rec(0x33u);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            tr.rec(0x34u);
+            const uint32_t xs_member_bytes = TILE_ROWS * DS_T * 4;
+            if (warp == 4 && lane == 0) {
+              // release this CTA's rows (cumulative over the CTA barrier above), then wait for the group
+              asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(p.flags + owner) : "memory");
+              const unsigned target = static_cast<unsigned>(nM) * static_cast<unsigned>(gstep + 1);
+              unsigned seen = 0, spins = 0;
+              do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.flags + owner) : "memory");
+                if (++spins > (1u << 26)) asm volatile("trap;");
+              } while (seen < target);
+              tr.rec(0x35u);
+              if (p.xs_bytes) {   // L2 -> shared memory, one bulk copy per member
+                asm volatile("fence.proxy.async;" ::: "memory");
+                mbar_arrive_expect_tx(bar_xs, xs_member_bytes * nM);
+                for (int m2 = 0; m2 < nM; ++m2)
+                  bulk_g2s(smem_base + lay.xs + m2 * xs_member_bytes, base + static_cast<size_t>(m2) * (TILE_ROWS * DS_T), xs_member_bytes, bar_xs);
+              }
+            }
+            float acc[DS_T];
+#pragma unroll
+            for (int i = 0; i < DS_T; ++i) acc[i] = 0.0f;
+            if (p.xs_bytes) {
+              mbar_wait(bar_xs, static_cast<uint32_t>(gstep & 1), dbgp, 0x7000000u);
+              tr.rec(0x36u);
+              const float4* xs = reinterpret_cast<const float4*>(smem + lay.xs) + row_in_tile * (DS_T / 4);
+#pragma unroll 1
+              for (int m2 = 0; m2 < nM; ++m2) {
+#pragma unroll
+                for (int c = 0; c < DS_T / 4; ++c) {
+                  const float4 v = xs[m2 * (TILE_ROWS * DS_T / 4) + c];
+                  acc[4 * c] = __fadd_rn(acc[4 * c], v.x); acc[4 * c + 1] = __fadd_rn(acc[4 * c + 1], v.y);
+                  acc[4 * c + 2] = __fadd_rn(acc[4 * c + 2], v.z); acc[4 * c + 3] = __fadd_rn(acc[4 * c + 3], v.w);
+                }
+              }
+              // every state thread is done with the staging area before the next step's copies may land:
+              // guaranteed by the bar.sync at the top of the next exchange (the copies are issued after it).
+            } else {
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+              for (int m2 = 0; m2 < nM; ++m2) {
+                const float4* src = reinterpret_cast<const float4*>(base + (static_cast<size_t>(m2) * TILE_ROWS + row_in_tile) * DS_T);
+                float4 v[DS_T / 4];
+#pragma unroll
+                for (int c = 0; c < DS_T / 4; ++c) v[c] = __ldcg(src + c);
+#pragma unroll
+                for (int c = 0; c < DS_T / 4; ++c) {
+                  acc[4 * c] = __fadd_rn(acc[4 * c], v[c].x); acc[4 * c + 1] = __fadd_rn(acc[4 * c + 1], v[c].y);
+                  acc[4 * c + 2] = __fadd_rn(acc[4 * c + 2], v[c].z); acc[4 * c + 3] = __fadd_rn(acc[4 * c + 3], v[c].w);
+                }
+              }
+            }
+            tr.rec(0x37u);
+#pragma unroll
+            for (int i = 0; i < DS_T; ++i) r[i / 8][i % 8] = __float_as_uint(acc[i]);
+          }
           if (nM == 1 && Lo.act != BBMPC_ACT_NONE) {   // non-linear output layer (single model only): rare, kept out of line
 #pragma unroll
             for (int c = 0; c < DS_T / 8; ++c)
@@ -500,7 +595,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
         for (int i = 0; i < DS_T; ++i) s[i] = s2[i];
         tr.rec(0x31u);
       }
-      if (valid) {
+      if (valid && my_member == 0) {
         float r = isnan(ret) ? -1e6f : ret;  // deterministic.py:75-77
         if (p.penalty) r = __fsub_rn(r, p.penalty[row]);
         p.returns[row] = r;
@@ -520,7 +615,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
     for (long long st = 0; st < n_steps; ++st) {
       tr.arm(p.trace && blockIdx.x == 0 && lane == 0 && st == 1);
       int idx = 0;
-      for (int mm = 0; mm < nM; ++mm) {
+      for (int mm = 0; mm < nM_here; ++mm) {
         for (int l = 0; l + 1 < nL; ++l, ++idx) {
           const int Npad = cv[8 * l], N = cv[8 * l + 1], act = (p.xflags & 2) ? BBMPC_ACT_NONE : cv[8 * l + 2];
           const int n_a_chunks = cv[8 * l + 3], csplit = cv[8 * l + 4];
@@ -565,7 +660,13 @@ static int launch_t(bbmpc_ctx* ctx, const TcParams& p, int grid, size_t smem_byt
   auto kern = (p.trace || p.dbg) ? rollout_tc_kernel<DS_T, DU_T, true, -1>
                                  : (all_tanh ? rollout_tc_kernel<DS_T, DU_T, false, BBMPC_ACT_TANH> : rollout_tc_kernel<DS_T, DU_T, false, -1>);
   BB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-  kern<<<grid, TC_THREADS, smem_bytes, st>>>(p);
+  if (p.group_mode) {
+    // the CTAs of a group wait for each other every horizon step: all of them must be resident
+    void* args[] = {const_cast<TcParams*>(&p)};
+    BB_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(TC_THREADS), args, smem_bytes, st));
+  } else {
+    kern<<<grid, TC_THREADS, smem_bytes, st>>>(p);
+  }
   BB_LAUNCH_CHECK(ctx);
   if (p.trace) {
     cudaStreamSynchronize(st);
@@ -644,14 +745,46 @@ int launch_rollout_tc(bbmpc_ctx* ctx, const float* states, const float* actions,
   }
   p.stage_bytes = stage;
   const size_t budget = 227 * 1024;
+  // Ensembles run member-parallel: the n_members CTAs of a group share a tile.  The mode depends on the
+  // model only (never on P), so results are bit-identical for any population size / sharding.
+  const int nM = m.mlp.n_members;
+  const bool group = nM > 1 && nM <= ctx->sm_count && !getenv("BBMPC_NO_GROUPS");
+  p.group_mode = group ? 1 : 0;
+  p.jobs = group ? m.mlp.solo_jobs : m.mlp.jobs;          p.n_jobs = group ? m.mlp.solo_jobs_per_step : m.mlp.jobs_per_step;
+  p.table = group ? m.mlp.solo_table : m.mlp.chunk_table; p.n_table = group ? m.mlp.solo_groups_per_step : m.mlp.chunks_per_step;
+  {
+    const int ds_t = m.dU > 8 ? 32 : (m.dS <= 8 ? 8 : (m.dS <= 24 ? 24 : 32));   // DS_T of the kernel instance launched below
+    const int xs = nM * TILE_ROWS * ds_t * 4;
+    p.xs_bytes = (group && xs <= 64 * 1024 && !getenv("BBMPC_NO_XS")) ? xs : 0;
+  }
   int n_stages = TC_MAX_STAGES;
-  const int cps = m.mlp.chunks_per_step, jps = m.mlp.jobs_per_step;
-  while (n_stages > 2 && tc_layout(stage, n_stages, cps, jps).total > budget) --n_stages;
-  if (tc_layout(stage, n_stages, cps, jps).total > budget)
+  const int cps = p.n_table, jps = p.n_jobs;
+  while (n_stages > 2 && tc_layout(stage, n_stages, cps, jps, p.xs_bytes).total > budget) --n_stages;
+  if (tc_layout(stage, n_stages, cps, jps, p.xs_bytes).total > budget)
     return fail(ctx, BBMPC_EINVAL, "tensor-core path: shared memory budget exceeded");
   p.n_stages = n_stages;
-  const size_t smem_bytes = tc_layout(stage, n_stages, cps, jps).total;
-  const int grid = p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count;
+  const size_t smem_bytes = tc_layout(stage, n_stages, cps, jps, p.xs_bytes).total;
+  int grid = p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count;
+  if (group) {
+    int n_groups = ctx->sm_count / nM;
+    if (n_groups > p.n_tiles) n_groups = p.n_tiles;
+    grid = n_groups * nM;
+    const size_t need = static_cast<size_t>(n_groups) * 2 * nM * TILE_ROWS * 32;
+    if (ctx->tc_xchg_floats < need) {
+      BB_CUDA(ctx, cudaStreamSynchronize(st));
+      cudaFree(ctx->tc_xchg);
+      BB_CUDA(ctx, cudaMalloc(&ctx->tc_xchg, need * sizeof(float)));
+      ctx->tc_xchg_floats = need;
+    }
+    if (ctx->tc_flags_n < n_groups) {
+      BB_CUDA(ctx, cudaStreamSynchronize(st));
+      cudaFree(ctx->tc_flags);
+      BB_CUDA(ctx, cudaMalloc(&ctx->tc_flags, n_groups * sizeof(unsigned)));
+      ctx->tc_flags_n = n_groups;
+    }
+    BB_CUDA(ctx, cudaMemsetAsync(ctx->tc_flags, 0, n_groups * sizeof(unsigned), st));
+    p.xchg = ctx->tc_xchg; p.flags = ctx->tc_flags;
+  }
   if (m.dS <= 8 && m.dU <= 8) return launch_t<8, 8>(ctx, p, grid, smem_bytes, st);
   if (m.dS <= 24 && m.dU <= 8) return launch_t<24, 8>(ctx, p, grid, smem_bytes, st);
   if (m.dU <= 8) return launch_t<32, 8>(ctx, p, grid, smem_bytes, st);

@@ -5,6 +5,46 @@
 #include "tc05.cuh"
 using namespace tc05;
 
+
+// ---- packed fp32x2 helpers (sm_100: FADD2 / FMUL2 / FFMA2)
+__device__ __forceinline__ uint64_t pk(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// pair tanh (prescaled input) + Veltkamp hi/lo split, packed math.  LO_CVT: lo via cvt (XU) or Veltkamp (FMA pipe)
+template <bool LO_CVT>
+__device__ __forceinline__ void tanh_split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  float w0, w1, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w0) : "f"(-fabsf(x0)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w1) : "f"(-fabsf(x1)));
+  const uint64_t one = pk(1.0f, 1.0f);
+  const uint64_t d = add2(pk(w0, w1), one);
+  float d0, d1; upk(d, d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d0 * d1));
+  uint64_t y = fma2(mul2(pk(r, r), pk(d1, d0)), pk(2.0f, 2.0f), pk(-1.0f, -1.0f));
+  float y0, y1; upk(y, y0, y1);
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD8;" : "=f"(y0) : "f"(y0), "f"(x0));
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD8;" : "=f"(y1) : "f"(y1), "f"(x1));
+  y = pk(y0, y1);
+  const uint64_t k = pk(65537.0f, 65537.0f);
+  const uint64_t c = mul2(y, k);
+  const uint64_t h = sub2(c, sub2(c, y));
+  const uint64_t l = sub2(y, h);
+  float h0, h1, l0, l1; upk(h, h0, h1); upk(l, l0, l1);
+  asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(hi) : "r"(__float_as_uint(h0)), "r"(__float_as_uint(h1)));
+  if (LO_CVT) {
+    lo = pack_bf16x2(l0, l1);
+  } else {
+    const uint64_t c2 = mul2(l, k);
+    const uint64_t lh = sub2(c2, sub2(c2, l));
+    float a, b; upk(lh, a, b);
+    asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(lo) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b)));
+  }
+}
+
 template <int V>
 __global__ void probe(float* io, unsigned long long* out, int iters) {
   float v[16];
@@ -58,6 +98,12 @@ __global__ void probe(float* io, unsigned long long* out, int iters) {
       for (int j = 0; j < 8; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { v[2 * j] += __uint_as_float(hi[j]); v[2 * j + 1] += __uint_as_float(lo[j]); }
+    } else if (V == 7 || V == 8) {  // packed-math pair tanh + split; 7: lo via cvt, 8: lo via Veltkamp
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tanh_split_pair<V == 7>(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[2 * j] += __uint_as_float(hi[j]); v[2 * j + 1] += __uint_as_float(lo[j]); }
     } else if (V == 6) {  // split only
       uint32_t hi[8], lo[8];
 #pragma unroll
@@ -81,7 +127,7 @@ void run(const char* name, float* io, unsigned long long* d) {
     cudaDeviceSynchronize();
     unsigned long long h = 0;
     cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-    printf("%-28s warps/SMSP=%d: %7.1f clk/iter/warp  -> %7.1f clk per chunk per SMSP\n", name, wps, double(h) / 2000, double(h) / 2000 / wps);
+    printf("%-36s warps/SMSP=%d: %7.1f clk/iter/warp  -> %7.1f clk per chunk per SMSP\n", name, wps, double(h) / 2000, double(h) / 2000 / wps);
   }
 }
 
@@ -95,5 +141,7 @@ int main() {
   run<4>("64 lop3", io, d);
   run<5>("pair-tanh16 + split", io, d);
   run<6>("split16", io, d);
+  run<7>("packed pair-tanh16+split(cvt lo)", io, d);
+  run<8>("packed pair-tanh16+split(velt lo)", io, d);
   return 0;
 }
