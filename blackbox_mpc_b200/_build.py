@@ -15,8 +15,8 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libbbmpc.so")
 OBJ_DIR = os.path.join(CSRC, "build")
-SOURCES = ["context.cu", "rollout_simt.cu", "rollout_tc.cu", "optimizers.cu"]
-HEADERS = ["common.cuh", "device_fns.cuh", "tc05.cuh", "refit.cuh"]
+SOURCES = ["context.cu", "rollout_simt.cu", "rollout_tc.cu", "optimizers.cu", "cmaes.cu"]
+HEADERS = ["common.cuh", "device_fns.cuh", "tc05.cuh", "refit.cuh", "opt_state.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -59,7 +59,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB + ".tmp", *objs,
-           "-Xlinker", "--exclude-libs,ALL", "-cudart", "static"]
+           "-Xlinker", "--exclude-libs,ALL", "-cudart", "static", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

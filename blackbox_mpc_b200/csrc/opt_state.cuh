@@ -1,0 +1,54 @@
+// opt_state.cuh — the optimizer handle shared by optimizers.cu and cmaes.cu.
+#pragma once
+#include <vector>
+#include "common.cuh"
+
+struct bbmpc_opt {
+  bbmpc_ctx* ctx = nullptr;
+  bbmpc_opt_config cfg{};
+  int rank = 0, world = 1;
+  int p0 = 0, P_local = 0;        // this rank's slice [p0, p0 + P_local) of the population
+  int n_eval = 0;                 // rows of the population axis handed to the evaluator (SPSA: 2*P_local)
+  int HU = 0, AHU = 0;            // H*dU, A*H*dU
+  uint32_t act_call = 0;
+  int time_step = 0;
+  bool began = false;
+  // device state
+  float *d_lb = nullptr, *d_ub = nullptr;
+  float* d_state = nullptr;       // [A,dS]
+  float* d_samples = nullptr;     // [n_eval, A, H, dU]
+  float* d_returns = nullptr;     // [n_eval, A]
+  float* d_penalty = nullptr;     // [n_eval, A]
+  float* d_mean = nullptr;        // loop variable  [A,H,dU]
+  float* d_var = nullptr;         // loop variable  [A,H,dU] (CEM)
+  float* d_prev = nullptr;        // persistent "previous solution" / current parameters [A,H,dU]
+  float* d_var0 = nullptr;        // persistent solution variance [A,H,dU]
+  float* d_partial = nullptr;     // [partial_floats]
+  float* d_action = nullptr;      // [A,dU]
+  float* d_next = nullptr;        // [A,dS]
+  float* d_reward = nullptr;      // [A]
+  // PSO
+  float *d_v = nullptr, *d_pbx = nullptr, *d_pbr = nullptr, *d_gbx = nullptr, *d_gbr = nullptr, *d_sol = nullptr;
+  // CMA-ES
+  float *d_m = nullptr, *d_sigma = nullptr, *d_C = nullptr, *d_B = nullptr, *d_D = nullptr, *d_ps = nullptr,
+        *d_pc = nullptr, *d_z = nullptr, *d_BD = nullptr, *d_work = nullptr, *d_cma_w = nullptr;
+  double cma_consts[16] = {0};
+  // trace + pinned staging
+  float* trace = nullptr; int64_t trace_floats = 0;
+  float* h_pinned = nullptr;
+  std::vector<void*> owned;
+};
+
+
+namespace bbmpc {
+// CMA-ES (csrc/cmaes.cu): optimizers/cma_es.py behind the same begin / iter_local / iter_merge / finish protocol
+int cmaes_create(bbmpc_opt* o);
+void cmaes_destroy(bbmpc_opt* o);
+int cmaes_set_shard(bbmpc_opt* o);
+int cmaes_reset(bbmpc_opt* o, cudaStream_t st);
+int cmaes_iter_local(bbmpc_opt* o, int iter, float* partial, cudaStream_t st);
+int cmaes_iter_merge(bbmpc_opt* o, int iter, const float* partials, int world, cudaStream_t st);
+// shared kernels implemented in optimizers.cu
+void launch_penalty(const float* excess_sq, float* penalty, int64_t rows, int HU, cudaStream_t st);
+void launch_topk_partial(const float* returns, const float* samples, float* partial, int P_local, int p0, int A, int HU, int E, cudaStream_t st);
+}  // namespace bbmpc

@@ -13,45 +13,9 @@
 #include "common.cuh"
 #include "device_fns.cuh"
 #include "refit.cuh"
+#include "opt_state.cuh"
 
 using namespace bbmpc;
-
-// ============================================================================ handle
-struct bbmpc_opt {
-  bbmpc_ctx* ctx = nullptr;
-  bbmpc_opt_config cfg{};
-  int rank = 0, world = 1;
-  int p0 = 0, P_local = 0;        // this rank's slice [p0, p0 + P_local) of the population
-  int n_eval = 0;                 // rows of the population axis handed to the evaluator (SPSA: 2*P_local)
-  int HU = 0, AHU = 0;            // H*dU, A*H*dU
-  uint32_t act_call = 0;
-  int time_step = 0;
-  bool began = false;
-  // device state
-  float *d_lb = nullptr, *d_ub = nullptr;
-  float* d_state = nullptr;       // [A,dS]
-  float* d_samples = nullptr;     // [n_eval, A, H, dU]
-  float* d_returns = nullptr;     // [n_eval, A]
-  float* d_penalty = nullptr;     // [n_eval, A]
-  float* d_mean = nullptr;        // loop variable  [A,H,dU]
-  float* d_var = nullptr;         // loop variable  [A,H,dU] (CEM)
-  float* d_prev = nullptr;        // persistent "previous solution" / current parameters [A,H,dU]
-  float* d_var0 = nullptr;        // persistent solution variance [A,H,dU]
-  float* d_partial = nullptr;     // [partial_floats]
-  float* d_action = nullptr;      // [A,dU]
-  float* d_next = nullptr;        // [A,dS]
-  float* d_reward = nullptr;      // [A]
-  // PSO
-  float *d_v = nullptr, *d_pbx = nullptr, *d_pbr = nullptr, *d_gbx = nullptr, *d_gbr = nullptr, *d_sol = nullptr;
-  // CMA-ES
-  float *d_m = nullptr, *d_sigma = nullptr, *d_C = nullptr, *d_B = nullptr, *d_D = nullptr, *d_ps = nullptr,
-        *d_pc = nullptr, *d_z = nullptr, *d_BD = nullptr, *d_work = nullptr, *d_cma_w = nullptr;
-  double cma_consts[16] = {0};
-  // trace + pinned staging
-  float* trace = nullptr; int64_t trace_floats = 0;
-  float* h_pinned = nullptr;
-  std::vector<void*> owned;
-};
 
 namespace {
 
@@ -499,6 +463,16 @@ inline int grid_for(int64_t n, int block) { return static_cast<int>((n + block -
 
 }  // namespace
 
+namespace bbmpc {
+void launch_penalty(const float* excess_sq, float* penalty, int64_t rows, int HU, cudaStream_t st) {
+  penalty_kernel<<<grid_for(rows * 32, 256), 256, 0, st>>>(excess_sq, penalty, rows, HU);
+}
+void launch_topk_partial(const float* returns, const float* samples, float* partial, int P_local, int p0, int A, int HU, int E,
+                         cudaStream_t st) {
+  topk_partial_kernel<<<A, SEL_THREADS, 0, st>>>(returns, samples, partial, P_local, p0, A, HU, E);
+}
+}  // namespace bbmpc
+
 // ============================================================================ host orchestration
 static int partial_floats(const bbmpc_opt* o) {
   const int A = o->cfg.num_agents, HU = o->HU;
@@ -508,6 +482,7 @@ static int partial_floats(const bbmpc_opt* o) {
     case BBMPC_OPT_RANDOM_SEARCH: return A * (2 + HU);
     case BBMPC_OPT_PSO: return A * (2 + HU);
     case BBMPC_OPT_SPSA: return A * HU;
+    case BBMPC_OPT_CMAES: return o->cfg.num_elite * (2 + A * HU);
     default: return 0;
   }
 }
@@ -521,7 +496,6 @@ int bbmpc_opt_create(bbmpc_ctx* ctx, const bbmpc_opt_config* cfg, bbmpc_opt** ou
   *out = nullptr;
   const int P = cfg->population_size, A = cfg->num_agents, H = cfg->planning_horizon, dU = cfg->dU, dS = cfg->dS;
   if (cfg->kind < BBMPC_OPT_CEM || cfg->kind > BBMPC_OPT_CMAES) return fail(ctx, BBMPC_EINVAL, "unknown optimizer kind %d", cfg->kind);
-  if (cfg->kind == BBMPC_OPT_CMAES) return fail(ctx, BBMPC_EINVAL, "CMA-ES refit is not built into libbbmpc yet");
   if (P < 1 || A < 1 || H < 1 || dU < 1 || dS < 1 || dU > MAX_DU || dS > MAX_DS)
     return fail(ctx, BBMPC_EINVAL, "bad optimizer shape P=%d A=%d H=%d dS=%d dU=%d", P, A, H, dS, dU);
   if (!cfg->lb_host || !cfg->ub_host) return fail(ctx, BBMPC_EINVAL, "action bounds missing");
@@ -554,6 +528,7 @@ int bbmpc_opt_create(bbmpc_ctx* ctx, const bbmpc_opt_config* cfg, bbmpc_opt** ou
     cudaMemset(o->d_sol, 0, A * dU * sizeof(float));
   }
   if ((rc = set_shard(o, 0, 1)) != BBMPC_OK) { bbmpc_opt_destroy(o); return rc; }
+  if (cfg->kind == BBMPC_OPT_CMAES && (rc = cmaes_create(o)) != BBMPC_OK) { bbmpc_opt_destroy(o); return rc; }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { rc = fail(ctx, BBMPC_ECUDA, "optimizer init: %s", cudaGetErrorString(e)); bbmpc_opt_destroy(o); return rc; }
   *out = o;
@@ -591,6 +566,7 @@ static int set_shard(bbmpc_opt* o, int rank, int world) {
   A_(dalloc(o, &o->d_partial, static_cast<size_t>(partial_floats(o))));
   if (o->cfg.kind == BBMPC_OPT_PI2 || o->cfg.kind == BBMPC_OPT_SPSA || o->cfg.kind == BBMPC_OPT_PSO)
     A_(dalloc(o, &o->d_work, rows * o->HU));
+  if (o->cfg.kind == BBMPC_OPT_CMAES) A_(cmaes_set_shard(o));
   if (o->cfg.kind == BBMPC_OPT_PSO) {
     A_(dalloc(o, &o->d_v, rows * o->HU)); A_(dalloc(o, &o->d_pbx, rows * o->HU)); A_(dalloc(o, &o->d_pbr, rows));
     if (rc == BBMPC_OK) {
@@ -638,6 +614,8 @@ int bbmpc_opt_reset(bbmpc_opt* o, void* stream) {
       o->act_call++;  // a reset consumes its own Philox sub-stream
       break;
     }
+    case BBMPC_OPT_CMAES:
+      return cmaes_reset(o, st);
     default: break;  // RandomSearch: nothing
   }
   return BBMPC_OK;
@@ -678,6 +656,7 @@ int bbmpc_opt_iter_local(bbmpc_opt* o, int iter, float* partial_out, void* strea
   const bbmpc_opt_config& c = o->cfg;
   const int A = c.num_agents, H = c.planning_horizon, dU = c.dU, HU = o->HU;
   float* partial = partial_out ? partial_out : o->d_partial;
+  if (c.kind == BBMPC_OPT_CMAES) return cmaes_iter_local(o, iter, partial, st);
   SampleArgs s{o->d_samples, o->d_penalty, o->d_mean, o->d_var, o->d_lb, o->d_ub, o->P_local, o->p0, A, H, dU,
                ctx->seed, o->act_call, static_cast<uint32_t>(iter), 0.0f, nullptr};
   const int64_t rows = static_cast<int64_t>(o->n_eval) * A;
@@ -755,6 +734,7 @@ int bbmpc_opt_iter_merge(bbmpc_opt* o, int iter, const float* partials, int worl
   const int A = c.num_agents, HU = o->HU;
   const float* in = partials ? partials : o->d_partial;
   const int64_t stride = partial_floats(o);
+  if (c.kind == BBMPC_OPT_CMAES) return cmaes_iter_merge(o, iter, in, world, st);
   switch (c.kind) {
     case BBMPC_OPT_CEM:
       if (world * c.num_elite > SEL_MAX_K) return opt_fail(o, BBMPC_EINVAL, "world*num_elite exceeds 1024");
@@ -883,6 +863,16 @@ int64_t bbmpc_opt_get_tensor(bbmpc_opt* o, const char* name, float* out, int64_t
   else if (s == "pbest_r") { src = o->d_pbr; n = pop; }
   else if (s == "gbest_x") { src = o->d_gbx; n = o->AHU; }
   else if (s == "gbest_r") { src = o->d_gbr; n = A; }
+  if (o->cfg.kind == BBMPC_OPT_CMAES) {   // tf.Variables of cma_es.py:95-117 (D as its diagonal)
+    const int64_t N = o->AHU;
+    if (s == "m") { src = o->d_mean; n = N; }
+    else if (s == "sigma") { src = o->d_sigma; n = N; }
+    else if (s == "C") { src = o->d_C; n = N * N; }
+    else if (s == "B") { src = o->d_B; n = N * N; }
+    else if (s == "D") { src = o->d_D; n = N; }
+    else if (s == "p_sigma") { src = o->d_ps; n = N; }
+    else if (s == "p_C") { src = o->d_pc; n = N; }
+  }
   if (!src) return fail(ctx, BBMPC_EINVAL, "unknown or unavailable tensor '%s'", name);
   if (out && n_floats > 0) {
     const int64_t m = n_floats < n ? n_floats : n;

@@ -1,5 +1,9 @@
-"""CMAESOptimizer (blackbox_mpc/optimizers/cma_es.py:6-227) — constructor surface only in this
-round; the covariance refit kernels are the next row of SURVEY §8 (a16)."""
+"""CMAESOptimizer (blackbox_mpc/optimizers/cma_es.py:6-227).  Runs entirely inside libbbmpc
+(csrc/cmaes.cu): fused Philox + `z @ (B D)` sampling GEMM, rollout, exact global top-E, evolution
+paths / per-coordinate step size / rank-one + rank-mu covariance update on the E elite rows (the
+reference materialises a [P,N,N] tensor there), symmetric eigendecomposition (cuSOLVER syevd).
+State (`m`, `sigma`, `C`, `B`, `D`, `p_sigma`, `p_C`) persists across act() calls; reset() restores
+`m` and `sigma` only, as the reference does.  `get_tensor("D")` is the diagonal of D."""
 from .. import _lib
 from .optimizer_base import OptimizerBase
 

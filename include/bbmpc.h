@@ -169,12 +169,14 @@ int bbmpc_opt_finish(bbmpc_opt* opt, int add_exploration_noise, float* action, f
 
 /* Test/inspection hooks.  name: "mean" "variance" (CEM/PI2), "solution" (SPSA), "samples"
  * (last iteration's local samples [P_local,A,H,dU]), "returns" ([P_local,A], penalties applied),
- * "m" "sigma" "C" "B" "D" "p_sigma" "p_C" (CMA-ES), "x" "v" "pbest_x" "pbest_r" "gbest_x" (PSO).
+ * "m" "sigma" "C" "B" "D" (diagonal) "p_sigma" "p_C" (CMA-ES), "x" "v" "pbest_x" "pbest_r" "gbest_x" (PSO).
  * Copies min(n_floats, size) floats into out (device) and returns the tensor's size in floats. */
 int64_t bbmpc_opt_get_tensor(bbmpc_opt* opt, const char* name, float* out, int64_t n_floats,
                              void* stream);
 /* When set (device buffer of n_iters*P_local*A*H*dU floats), every iteration's evaluated samples
- * are also recorded there, so a test can inject the exact draws into the oracle.  NULL disables. */
+ * are also recorded there, so a test can inject the exact draws into the oracle.  NULL disables.
+ * CMA-ES records its raw N(0,1) draws z [P_local, N] per iteration instead (the samples follow from z
+ * through the solver-specific eigenbasis B). */
 int bbmpc_opt_set_sample_trace(bbmpc_opt* opt, float* trace, int64_t n_floats);
 
 /* ---- sampler known-answer hooks (host-side, no GPU needed) -------------------------------- */
