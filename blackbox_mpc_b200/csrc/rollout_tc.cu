@@ -48,6 +48,9 @@ constexpr int TC_MAX_STAGES = 24;
 constexpr int TC_MAX_CHUNKS = 16;   // K chunks of one layer (Kpad <= 256)
 constexpr int TILE_ROWS = 128;
 constexpr int MAX_DU_T = 16;
+#ifndef EPI_STAGGER
+#define EPI_STAGGER 250   // clocks between the first chunks of the conversion warps of a quarter
+#endif
 
 struct TcParams {
   MlpDev mlp;
@@ -82,9 +85,10 @@ __host__ __device__ inline TcSmemLayout tc_layout(int stage_bytes, int n_stages,
   off = (off + 15u) & ~15u;
   L.jobs = off;   off += static_cast<uint32_t>(jobs_per_step) * sizeof(TcJob);
   L.bars = off;   off += TC_NUM_BARS * 8;
+  off = (off + 15u) & ~15u;
   L.tmem_slot = off; off += 16;
   L.stats = off;  off += (4 * MAX_DS + 2 * MAX_DU) * 4;
-  L.conv = off;   off += MAX_LAYERS * 32;
+  L.conv = off;   off += MAX_LAYERS * (32 + 256);   // per hidden layer: 8 ints + mask/add vectors of its 2 trailing chunks
   L.total = off;
   return L;
 }
@@ -158,21 +162,28 @@ __device__ __forceinline__ void convert_full(uint32_t taddr, int c, int passes) 
   act16<ACT>(v);
   store_split(taddr, c, v, passes);
 }
+// The (at most two) trailing chunks of a layer hold real features, the three ones-columns that meet the
+// bias rows of the next layer's weights, and zero padding: v = act(D) * mask + add with per-column
+// mask / add vectors prepared in shared memory (no per-column tests in the instruction stream).
 template <int ACT>
-__device__ __noinline__ void convert_edge(uint32_t taddr, int c, int Npad, int N, int passes) {
+__device__ __forceinline__ void convert_tail(uint32_t taddr, int c, bool has_data, const float* mk_ad, int passes) {
   float v[16];
-  if (16 * c < Npad) {
+  if (has_data) {
     uint32_t r[16];
     tmem_ld16(taddr + 16 * c, r);
     wait_ld();
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
     act16<ACT>(v);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.0f;
   }
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int f = 16 * c + j;
-    if (f >= N || 16 * c >= Npad) v[j] = (f >= N && f < N + BIAS_COLS) ? 1.0f : 0.0f;
+  for (int j = 0; j < 16; j += 4) {
+    const float4 mk = *reinterpret_cast<const float4*>(mk_ad + j), ad = *reinterpret_cast<const float4*>(mk_ad + 16 + j);
+    v[j] = fmaf(v[j], mk.x, ad.x); v[j + 1] = fmaf(v[j + 1], mk.y, ad.y);
+    v[j + 2] = fmaf(v[j + 2], mk.z, ad.z); v[j + 3] = fmaf(v[j + 3], mk.w, ad.w);
   }
   store_split(taddr, c, v, passes);
 }
@@ -182,12 +193,19 @@ __device__ __noinline__ void convert_edge(uint32_t taddr, int c, int Npad, int N
 // arrival on the mbarrier of the chunk's UNIT (pair of chunks, the MMA issuer's wait granularity).
 template <int ACT, bool TR>
 __device__ __forceinline__ void epi_hidden(uint32_t taddr, int Npad, int N, int n_a_chunks, int cb, int ce, int sub,
-                                           int passes, uint32_t bar_unit, int lane, Tracer<TR>& tr) {
+                                           int passes, uint32_t bar_unit, int lane, const float* tail_tab, Tracer<TR>& tr) {
   const int n_full = N >> 4;   // chunks whose 16 columns are all real features
+  if (EPI_STAGGER > 0 && sub > 0) {
+    // The EPI_SUB warps of a quarter share one MUFU pipe; started together they finish their chunks in
+    // bursts and the MMA issuer idles, then has a whole round of chunks left when the epilogue is done.
+    // A small start offset per warp makes the chunks complete at a steady rate instead.
+    const long long t0 = clock64();
+    while (clock64() - t0 < static_cast<long long>(sub) * EPI_STAGGER) {}
+  }
   for (int c = cb + ((sub - cb) & (EPI_SUB - 1)); c < ce; c += EPI_SUB) {   // chunks of [cb, ce) with c % EPI_SUB == sub
     tr.rec(0x100u | c);
     if (c < n_full) convert_full<ACT>(taddr, c, passes);
-    else convert_edge<ACT>(taddr, c, Npad, N, passes);
+    else convert_tail<ACT>(taddr, c, 16 * c < Npad, tail_tab + 32 * (c - n_full), passes);
     tr.rec(0x300u | c);
     wait_st();
     fence_before_sync();
@@ -269,6 +287,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
       cv[8 * l + 0] = M.layer[l].Npad; cv[8 * l + 1] = M.layer[l].N; cv[8 * l + 2] = M.layer[l].act;
       cv[8 * l + 3] = M.layer[l + 1].Kpad >> 4;                  // A-operand chunks of the next layer
       cv[8 * l + 4] = M.layer[l].nsplit >> 4;                    // first chunk of column half 1 (0: not split)
+      float* tt = reinterpret_cast<float*>(smem + lay.conv + MAX_LAYERS * 32) + 64 * l;
+      const int N = M.layer[l].N, f0 = (N >> 4) << 4;
+      for (int q2 = 0; q2 < 2; ++q2)
+        for (int j = 0; j < 16; ++j) {
+          const int f = f0 + 16 * q2 + j;
+          tt[32 * q2 + j] = f < N ? 1.0f : 0.0f;                                   // mask
+          tt[32 * q2 + 16 + j] = (f >= N && f < N + BIAS_COLS) ? 1.0f : 0.0f;      // add
+        }
     }
   }
   if (warp == 2) {
@@ -619,6 +645,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
         for (int l = 0; l + 1 < nL; ++l, ++idx) {
           const int Npad = cv[8 * l], N = cv[8 * l + 1], act = (p.xflags & 2) ? BBMPC_ACT_NONE : cv[8 * l + 2];
           const int n_a_chunks = cv[8 * l + 3], csplit = cv[8 * l + 4];
+          const float* tail_tab = reinterpret_cast<const float*>(smem + lay.conv + MAX_LAYERS * 32) + 64 * l;
           const uint32_t taddr = tm + ((idx & 1) ? p.col_buf1 : p.col_buf0);
           const uint32_t bar_set = bar_achunk + 8 * ((rj & 1u) * TC_MAX_CHUNKS);
           ++rj;
@@ -630,13 +657,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
             tr.rec(0x20u | (mm << 12) | (l << 8) | (h << 6));
             const int cb = h ? csplit : 0, ce = (csplit && !h) ? csplit : n_a_chunks;
             if (ACT_T >= 0) {
-              epi_hidden<(ACT_T >= 0 ? ACT_T : 0), TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tr);
+              epi_hidden<(ACT_T >= 0 ? ACT_T : 0), TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tail_tab, tr);
             } else {
               switch (act) {
-                case BBMPC_ACT_TANH: epi_hidden<BBMPC_ACT_TANH, TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tr); break;
-                case BBMPC_ACT_RELU: epi_hidden<BBMPC_ACT_RELU, TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tr); break;
-                case BBMPC_ACT_SIGMOID: epi_hidden<BBMPC_ACT_SIGMOID, TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tr); break;
-                default: epi_hidden<BBMPC_ACT_NONE, TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tr); break;
+                case BBMPC_ACT_TANH: epi_hidden<BBMPC_ACT_TANH, TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tail_tab, tr); break;
+                case BBMPC_ACT_RELU: epi_hidden<BBMPC_ACT_RELU, TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tail_tab, tr); break;
+                case BBMPC_ACT_SIGMOID: epi_hidden<BBMPC_ACT_SIGMOID, TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tail_tab, tr); break;
+                default: epi_hidden<BBMPC_ACT_NONE, TR>(taddr, Npad, N, n_a_chunks, cb, ce, sub, p.passes, bar_set, lane, tail_tab, tr); break;
               }
             }
           }
