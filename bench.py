@@ -31,6 +31,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+print_json = print
 METRIC = "mpc_steps_per_sec"
 UNIT = "steps/s"
 
@@ -182,7 +183,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print_json(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------- our arm
@@ -311,12 +312,24 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     elif world > 1:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    print_json(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def _json_only_stdout():
+    """The driver reads ONE JSON line from stdout; libraries (NCCL's version banner, torch warnings) may
+    print there too.  Point fd 1 at stderr for the whole run and return a writer for the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return lambda text: os.write(real, (text + "\n").encode())
+
+
 def main():
+    emit = _json_only_stdout()
+    global print_json
+    print_json = emit
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -7,7 +7,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbbmpc.so")
+LIB_PATH = os.environ.get("BBMPC_LIB") or os.path.join(_HERE, "libbbmpc.so")   # BBMPC_LIB: A/B builds (tools/debug)
 
 # mirrors of include/bbmpc.h
 OK, EINVAL, ECUDA, ESTATE, ENOMEM = 0, -1, -2, -3, -4

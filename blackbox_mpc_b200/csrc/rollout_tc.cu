@@ -37,13 +37,17 @@
 namespace bbmpc {
 using namespace tc05;
 
-static_assert(true, "");
-constexpr int EPI_SUB = 4;                      // conversion warps per TMEM lane quarter
+// 3 conversion warps per quarter => 640 threads => 96 registers per thread: measured faster than 4 warps
+// at 80 registers (the state warps spill less) and on par with 2 warps at 128 (tools/debug/ab.sh, r1c).
+#ifndef BBMPC_EPI_SUB
+#define BBMPC_EPI_SUB 3
+#endif
+constexpr int EPI_SUB = BBMPC_EPI_SUB;                      // conversion warps per TMEM lane quarter
 constexpr int EPI_WARPS = 4 * EPI_SUB;
 constexpr int TC_WARPS = 8 + EPI_WARPS;         // warpgroup 0: producer, MMA issuer, TMEM owner, idle; warpgroup 1: state warps
 constexpr int TC_THREADS = 32 * TC_WARPS;
-// (768 threads -> 80 registers per thread; ptxas does not raise the cap after setmaxnreg.inc, so every
-// role is written to fit 80 registers and no setmaxnreg is used.)
+// (640 threads -> 96 registers per thread; ptxas does not raise the cap after setmaxnreg.inc, so every
+// role is written to fit 96 registers and no setmaxnreg is used.)
 constexpr int TC_MAX_STAGES = 24;
 constexpr int TC_MAX_CHUNKS = 16;   // K chunks of one layer (Kpad <= 256)
 constexpr int TILE_ROWS = 128;
@@ -110,6 +114,14 @@ __device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok;
+}
+
+// Busy-polling wait (non-blocking test_wait): a suspended try_wait wakes up ~500 cycles after the phase
+// completes (measured with the in-kernel tracer); a single polling warp on the critical path reacts within
+// one probe latency (~100 cycles) at the price of a few issue slots.
+__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) { if (++spins > (1u << 26)) asm volatile("trap;"); }
 }
 
 // tanh of two pre-activations that arrive PRE-SCALED by 2 log2(e) (the scale is folded into the
@@ -202,7 +214,7 @@ __device__ __forceinline__ void epi_hidden(uint32_t taddr, int Npad, int N, int 
     const long long t0 = clock64();
     while (clock64() - t0 < static_cast<long long>(sub) * EPI_STAGGER) {}
   }
-  for (int c = cb + ((sub - cb) & (EPI_SUB - 1)); c < ce; c += EPI_SUB) {   // chunks of [cb, ce) with c % EPI_SUB == sub
+  for (int c = cb + ((sub - cb % EPI_SUB + EPI_SUB) % EPI_SUB); c < ce; c += EPI_SUB) {   // chunks of [cb, ce) with c % EPI_SUB == sub
     tr.rec(0x100u | c);
     if (c < n_full) convert_full<ACT>(taddr, c, passes);
     else convert_tail<ACT>(taddr, c, 16 * c < Npad, tail_tab + 32 * (c - n_full), passes);
@@ -370,7 +382,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
             const uint32_t sbase = (stages16 + stage * stage16);
             for (uint32_t k = 0; k < n; ++k, ++u) {
               if (from_epi) {
-                if (!pre_ok) mbar_wait(bar_c + 8 * u, (cph >> u) & 1u, dbgp, 0x2000000u | (j << 8) | u);
+                if (!pre_ok) {
+                  if (p.xflags & 8) mbar_wait(bar_c + 8 * u, (cph >> u) & 1u, dbgp, 0x2000000u | (j << 8) | u);
+                  else mbar_wait_poll(bar_c + 8 * u, (cph >> u) & 1u);
+                }
                 pre_ok = (u + 1 < n_units) ? mbar_test_wait(bar_c + 8 * (u + 1), (cph >> (u + 1)) & 1u) : 0u;
               }
               fence_after_sync();

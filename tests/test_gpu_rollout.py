@@ -106,3 +106,23 @@ def test_full_size_properties(cuda_device):
     _, ev32 = _policy_and_eval(w, "fp32")
     r32 = ev32(state, actions, 0).cpu()
     helpers.compare_returns(r.numpy(), r32.numpy(), max_jump_frac=0.02, **TOL["bf16x3"])
+
+
+@pytest.mark.parametrize("P,A", [(700, 1), (130, 3), (20000, 1)])
+def test_member_parallel_matches_single_cta(cuda_device, monkeypatch, P, A):
+    """Ensembles run member-parallel (n_members CTAs share a tile and exchange their raw outputs every
+    horizon step); BBMPC_NO_GROUPS=1 forces the one-CTA-per-tile pipeline.  Both contract the same
+    products; they differ only in where the member sum is formed (fp32 adds vs the TMEM accumulator).
+    Covers ragged last tiles, several agents and more tiles than groups (several rounds per group)."""
+    w = workloads.make("C4", population_size=P, num_agents=A, bias_scale=0.1)
+    _, ev = _policy_and_eval(w, "bf16x3")
+    actions = helpers.random_actions(w, P, seed=11)
+    state = torch.from_numpy(w.state)
+    r_group = ev(state, actions, 0).cpu().numpy()
+    r_again = ev(state, actions, 0).cpu().numpy()
+    assert np.array_equal(r_group, r_again)                 # deterministic exchange
+    monkeypatch.setenv("BBMPC_NO_GROUPS", "1")
+    r_single = ev(state, actions, 0).cpu().numpy()
+    monkeypatch.delenv("BBMPC_NO_GROUPS")
+    assert np.isfinite(r_group).all()
+    helpers.compare_returns(r_group, r_single, max_jump_frac=0.02, **TOL["bf16x3"])
