@@ -116,6 +116,7 @@ struct bbmpc_ctx {
   // member-parallel rollout: per-group exchange of the members' raw outputs + arrival counters
   float* tc_xchg = nullptr; size_t tc_xchg_floats = 0;
   unsigned* tc_flags = nullptr; int tc_flags_n = 0;
+  bool tc_no_groups = false;   // a cooperative launch did not fit: stay with one CTA per tile
   void* dbg_host = nullptr;  // BBMPC_DEBUG=1: host-mapped watchdog record of the tensor-core kernel
   // rollout-kernel timing (bbmpc_profile_*): event pairs recorded around every rollout launch
   bool prof_on = false;

@@ -51,6 +51,7 @@ constexpr int TC_THREADS = 32 * TC_WARPS;
 constexpr int TC_MAX_STAGES = 24;
 constexpr int TC_MAX_CHUNKS = 16;   // K chunks of one layer (Kpad <= 256)
 constexpr int TILE_ROWS = 128;
+constexpr int BBMPC_ERETRY = -100;   // internal: relaunch with the member-parallel mode disabled
 constexpr int MAX_DU_T = 16;
 #ifndef EPI_STAGGER
 #define EPI_STAGGER 250   // clocks between the first chunks of the conversion warps of a quarter
@@ -705,7 +706,13 @@ static int launch_t(bbmpc_ctx* ctx, const TcParams& p, int grid, size_t smem_byt
   if (p.group_mode) {
     // the CTAs of a group wait for each other every horizon step: all of them must be resident
     void* args[] = {const_cast<TcParams*>(&p)};
-    BB_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(TC_THREADS), args, smem_bytes, st));
+    const cudaError_t ce = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(TC_THREADS), args, smem_bytes, st);
+    if (ce == cudaErrorCooperativeLaunchTooLarge) {   // fewer SMs than expected (MPS / green context): one CTA per tile instead
+      cudaGetLastError();
+      ctx->tc_no_groups = true;
+      return BBMPC_ERETRY;
+    }
+    BB_CUDA(ctx, ce);
   } else {
     kern<<<grid, TC_THREADS, smem_bytes, st>>>(p);
   }
@@ -758,8 +765,16 @@ bool tc_column_map(const MlpDev& m, int* buf_w, int* col_x, int* col_dout) {
   return w + x_w <= 256 && w + (out_w > 32 ? out_w : 32) <= 256;
 }
 
+static int launch_rollout_tc_once(bbmpc_ctx* ctx, const float* states, const float* actions, float* returns,
+                                  const float* penalty, int rows, int A, int H, int passes, cudaStream_t st);
 int launch_rollout_tc(bbmpc_ctx* ctx, const float* states, const float* actions, float* returns,
                       const float* penalty, int rows, int A, int H, int passes, cudaStream_t st) {
+  int rc = launch_rollout_tc_once(ctx, states, actions, returns, penalty, rows, A, H, passes, st);
+  if (rc == BBMPC_ERETRY) rc = launch_rollout_tc_once(ctx, states, actions, returns, penalty, rows, A, H, passes, st);
+  return rc;
+}
+static int launch_rollout_tc_once(bbmpc_ctx* ctx, const float* states, const float* actions, float* returns,
+                                  const float* penalty, int rows, int A, int H, int passes, cudaStream_t st) {
   const ModelHost& m = ctx->model;
   TcParams p{};
   p.mlp = m.mlp; p.norm = m.norm; p.reward_id = ctx->reward_id; p.dS = m.dS; p.dU = m.dU;
@@ -790,7 +805,7 @@ int launch_rollout_tc(bbmpc_ctx* ctx, const float* states, const float* actions,
   // Ensembles run member-parallel: the n_members CTAs of a group share a tile.  The mode depends on the
   // model only (never on P), so results are bit-identical for any population size / sharding.
   const int nM = m.mlp.n_members;
-  const bool group = nM > 1 && nM <= ctx->sm_count && !getenv("BBMPC_NO_GROUPS");
+  const bool group = nM > 1 && nM <= ctx->sm_count && !ctx->tc_no_groups && !getenv("BBMPC_NO_GROUPS");
   p.group_mode = group ? 1 : 0;
   p.jobs = group ? m.mlp.solo_jobs : m.mlp.jobs;          p.n_jobs = group ? m.mlp.solo_jobs_per_step : m.mlp.jobs_per_step;
   p.table = group ? m.mlp.solo_table : m.mlp.chunk_table; p.n_table = group ? m.mlp.solo_groups_per_step : m.mlp.chunks_per_step;
