@@ -53,6 +53,10 @@ constexpr int TC_MAX_CHUNKS = 16;   // K chunks of one layer (Kpad <= 256)
 constexpr int TILE_ROWS = 128;
 constexpr int BBMPC_ERETRY = -100;   // internal: relaunch with the member-parallel mode disabled
 constexpr int MAX_DU_T = 16;
+#ifndef BBMPC_PACKED_TANH
+#define BBMPC_PACKED_TANH 1
+#endif
+constexpr bool PACKED_TANH = BBMPC_PACKED_TANH != 0;   // quad-shared reciprocal + packed fp32x2 epilogue math
 #ifndef EPI_STAGGER
 #define EPI_STAGGER 250   // clocks between the first chunks of the conversion warps of a quarter
 #endif
@@ -142,6 +146,38 @@ __device__ __forceinline__ void tanh_pair_prescaled(float& x0, float& x1) {
   asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD8;" : "=f"(x1) : "f"(y1), "f"(x1));
 }
 
+// tanh of FOUR pre-scaled pre-activations with 4 MUFU.EX2 + ONE MUFU.RCP, then bf16 hi/lo split, all FMA-pipe
+// work as packed fp32x2: d_i = 1 + 2^-|t_i| in (1, 2]; r = 1/(d0 d1 d2 d3) (product <= 16); 1/d0 = r (d1 d3) d2,
+// 1/d1 = r (d0 d2) d3, 1/d2 = r (d1 d3) d0, 1/d3 = r (d0 d2) d1.  1.25 MUFU per element.
+__device__ __forceinline__ void tanh_split_quad(float x0, float x1, float x2, float x3, uint32_t& hi01, uint32_t& lo01,
+                                                uint32_t& hi23, uint32_t& lo23) {
+  float w0, w1, w2, w3, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w0) : "f"(-fabsf(x0)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w1) : "f"(-fabsf(x1)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w2) : "f"(-fabsf(x2)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w3) : "f"(-fabsf(x3)));
+  const uint64_t one = pk2(1.0f, 1.0f);
+  const uint64_t d01 = add2(pk2(w0, w1), one), d23 = add2(pk2(w2, w3), one);
+  const uint64_t p = mul2(d01, d23);                 // (d0 d2, d1 d3)
+  float px, py;
+  upk2(p, px, py);
+  const float P = px * py;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(P));
+  r = fmaf(r, fmaf(-P, r, 1.0f), r);                  // one Newton step: the shared reciprocal feeds four results
+  const uint64_t t = mul2(pk2(r, r), pk2(py, px));    // (r d1 d3, r d0 d2)
+  const uint64_t two = pk2(2.0f, 2.0f), m1 = pk2(-1.0f, -1.0f);
+  uint64_t y01 = fma2(mul2(t, d23), two, m1);         // 2/d0 - 1, 2/d1 - 1
+  uint64_t y23 = fma2(mul2(t, d01), two, m1);         // 2/d2 - 1, 2/d3 - 1
+  float y0, y1, y2, y3;
+  upk2(y01, y0, y1); upk2(y23, y2, y3);
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD8;" : "=f"(y0) : "f"(y0), "f"(x0));   // copysign
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD8;" : "=f"(y1) : "f"(y1), "f"(x1));
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD8;" : "=f"(y2) : "f"(y2), "f"(x2));
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD8;" : "=f"(y3) : "f"(y3), "f"(x3));
+  split_bf16x2_packed(pk2(y0, y1), hi01, lo01);
+  split_bf16x2_packed(pk2(y2, y3), hi23, lo23);
+}
+
 template <int ACT>
 __device__ __forceinline__ void act16(float (&v)[16]) {
   if (ACT == BBMPC_ACT_TANH) {
@@ -169,6 +205,16 @@ __device__ __forceinline__ void convert_full(uint32_t taddr, int c, int passes) 
   uint32_t r[16];
   tmem_ld16(taddr + 16 * c, r);
   wait_ld();
+  if (ACT == BBMPC_ACT_TANH && PACKED_TANH) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      tanh_split_quad(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]),
+                      hi[2 * j], lo[2 * j], hi[2 * j + 1], lo[2 * j + 1]);
+    tmem_st8(taddr + 16 * c, hi);
+    if (passes == 3) tmem_st8(taddr + 16 * c + 8, lo);
+    return;
+  }
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);

@@ -217,4 +217,27 @@ __device__ __forceinline__ void split_bf16x2_veltkamp(float a, float b, uint32_t
   lo = pack_bf16x2(__fsub_rn(a, ha), __fsub_rn(b, hb));
 }
 
+// ----------------------------------------------------------------------------- packed fp32x2 (FADD2 / FMUL2 / FFMA2)
+// Two fp32 lanes per instruction: halves the issue slots of the epilogue's FMA-pipe work.
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// Veltkamp hi/lo bf16 split of a packed pair (see split_bf16x2_veltkamp): 4 packed ops + prmt + one cvt.
+// Written as z = 2^16 y (exact), s = fl(y + z), hi = s - z (exact): ptxas contracts mul.rn.f32x2 + sub.rn.f32x2
+// into FFMA2 (it does not for the scalar .rn forms); in the textbook form c = 65537 y, hi = c - (c - y) that
+// contraction cancels the rounding (hi == y, lo == 0, measured), in this form every contraction is exact.
+__device__ __forceinline__ void split_bf16x2_packed(uint64_t y, uint32_t& hi, uint32_t& lo) {
+  const uint64_t z = mul2(y, pk2(65536.0f, 65536.0f));
+  const uint64_t h = sub2(add2(y, z), z);
+  const uint64_t l = sub2(y, h);
+  float h0, h1, l0, l1;
+  upk2(h, h0, h1); upk2(l, l0, l1);
+  asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(hi) : "r"(__float_as_uint(h0)), "r"(__float_as_uint(h1)));
+  lo = pack_bf16x2(l0, l1);
+}
+
 }  // namespace tc05

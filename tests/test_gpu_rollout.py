@@ -10,8 +10,10 @@ from blackbox_mpc_b200.utils import workloads
 pytestmark = pytest.mark.gpu
 
 # fp32 path: same arithmetic as the reference up to summation order.  bf16x3: operands carry 16
-# mantissa bits, products ~2^-17 relative; the recurrence amplifies that over H steps.
-TOL = {"fp32": dict(atol=2e-3, rtol=2e-5), "bf16x3": dict(atol=2e-2, rtol=2e-4)}
+# mantissa bits, products ~2^-17 relative; measured max |error| on H=30 returns of magnitude 10^2..10^3
+# is 2e-4..6e-4 (tools/debug/err_stats.py).  The bound is kept within ~10x of that: a systematic operand
+# error (e.g. a truncating instead of rounding hi/lo split: 4e-2) must fail.
+TOL = {"fp32": dict(atol=2e-3, rtol=2e-5), "bf16x3": dict(atol=3e-3, rtol=3e-5)}
 STEP_TOL = {"fp32": 2e-5, "bf16x3": 1e-4}
 
 

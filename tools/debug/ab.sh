@@ -2,7 +2,7 @@
 # A/B timing of rollout variants selected by environment knobs.
 B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline"
 ext() { python -c "import json,sys; d=json.loads([l for l in sys.stdin if l.startswith('{')][0]); print('$1', 'steps/s', round(d['value'],1), 'kernel_ms', round(d['roofline']['kernel_ms_avg'],3))"; }
-$B | ext base
-BBMPC_NSPLIT=1 $B | ext nsplit
-$B --population 1250 | ext base_P1250
-BBMPC_NSPLIT=1 $B --population 1250 | ext nsplit_P1250
+$B | ext packed
+BBMPC_LIB=$PWD/blackbox_mpc_b200/libbbmpc_np.so $B | ext scalar
+$B --population 1250 | ext packed_P1250
+BBMPC_LIB=$PWD/blackbox_mpc_b200/libbbmpc_np.so $B --population 1250 | ext scalar_P1250
