@@ -37,17 +37,18 @@
 namespace bbmpc {
 using namespace tc05;
 
-// 3 conversion warps per quarter => 640 threads => 96 registers per thread: measured faster than 4 warps
-// at 80 registers (the state warps spill less) and on par with 2 warps at 128 (tools/debug/ab.sh, r1c).
+// 2 conversion warps per quarter => 512 threads => 128 registers per thread.  Measured (tools/debug/ab.sh,
+// r1c, C4 rollout): 2 warps 1.40 ms, 3 warps (96 registers) 1.44 ms, 4 warps (80 registers, state warps
+// spill) 1.53 ms: the conversion is bound by the MUFU pipe of its SM sub-partition, not by warp count.
 #ifndef BBMPC_EPI_SUB
-#define BBMPC_EPI_SUB 3
+#define BBMPC_EPI_SUB 2
 #endif
 constexpr int EPI_SUB = BBMPC_EPI_SUB;                      // conversion warps per TMEM lane quarter
 constexpr int EPI_WARPS = 4 * EPI_SUB;
 constexpr int TC_WARPS = 8 + EPI_WARPS;         // warpgroup 0: producer, MMA issuer, TMEM owner, idle; warpgroup 1: state warps
 constexpr int TC_THREADS = 32 * TC_WARPS;
-// (640 threads -> 96 registers per thread; ptxas does not raise the cap after setmaxnreg.inc, so every
-// role is written to fit 96 registers and no setmaxnreg is used.)
+// (512 threads -> 128 registers per thread; ptxas does not raise the cap after setmaxnreg.inc, so every
+// role is written to fit 128 registers and no setmaxnreg is used.)
 constexpr int TC_MAX_STAGES = 24;
 constexpr int TC_MAX_CHUNKS = 16;   // K chunks of one layer (Kpad <= 256)
 constexpr int TILE_ROWS = 128;
@@ -201,11 +202,8 @@ __device__ __forceinline__ void store_split(uint32_t taddr, int c, const float (
   if (passes == 3) tmem_st8(taddr + 16 * c + 8, lo);
 }
 template <int ACT>
-__device__ __forceinline__ void convert_full(uint32_t taddr, int c, int passes) {
-  uint32_t r[16];
-  tmem_ld16(taddr + 16 * c, r);
-  wait_ld();
-  if (ACT == BBMPC_ACT_TANH && PACKED_TANH) {
+__device__ __forceinline__ void convert_full(uint32_t taddr, int c, const uint32_t (&r)[16], int passes) {
+  if constexpr (ACT == BBMPC_ACT_TANH && PACKED_TANH) {
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -213,13 +211,13 @@ __device__ __forceinline__ void convert_full(uint32_t taddr, int c, int passes) 
                       hi[2 * j], lo[2 * j], hi[2 * j + 1], lo[2 * j + 1]);
     tmem_st8(taddr + 16 * c, hi);
     if (passes == 3) tmem_st8(taddr + 16 * c + 8, lo);
-    return;
-  }
-  float v[16];
+  } else {
+    float v[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-  act16<ACT>(v);
-  store_split(taddr, c, v, passes);
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+    act16<ACT>(v);
+    store_split(taddr, c, v, passes);
+  }
 }
 // The (at most two) trailing chunks of a layer hold real features, the three ones-columns that meet the
 // bias rows of the next layer's weights, and zero padding: v = act(D) * mask + add with per-column
@@ -261,10 +259,18 @@ __device__ __forceinline__ void epi_hidden(uint32_t taddr, int Npad, int N, int 
     const long long t0 = clock64();
     while (clock64() - t0 < static_cast<long long>(sub) * EPI_STAGGER) {}
   }
+  // (processing whole units per iteration saves ~150 cycles of per-iteration overhead per chunk but coarsens the
+  // pipeline towards the MMA issuer: measured slower, 1.45 vs 1.39 ms)
   for (int c = cb + ((sub - cb % EPI_SUB + EPI_SUB) % EPI_SUB); c < ce; c += EPI_SUB) {   // chunks of [cb, ce) with c % EPI_SUB == sub
     tr.rec(0x100u | c);
-    if (c < n_full) convert_full<ACT>(taddr, c, passes);
-    else convert_tail<ACT>(taddr, c, 16 * c < Npad, tail_tab + 32 * (c - n_full), passes);
+    if (c < n_full) {
+      uint32_t r[16];
+      tmem_ld16(taddr + 16 * c, r);
+      wait_ld();
+      convert_full<ACT>(taddr, c, r, passes);
+    } else {
+      convert_tail<ACT>(taddr, c, 16 * c < Npad, tail_tab + 32 * (c - n_full), passes);
+    }
     tr.rec(0x300u | c);
     wait_st();
     fence_before_sync();
