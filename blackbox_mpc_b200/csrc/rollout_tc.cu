@@ -59,7 +59,7 @@ constexpr int MAX_DU_T = 16;
 #endif
 constexpr bool PACKED_TANH = BBMPC_PACKED_TANH != 0;   // quad-shared reciprocal + packed fp32x2 epilogue math
 #ifndef EPI_STAGGER
-#define EPI_STAGGER 250   // clocks between the first chunks of the conversion warps of a quarter
+#define EPI_STAGGER 150   // clocks between the first chunks of the conversion warps of a quarter
 #endif
 
 struct TcParams {
