@@ -258,6 +258,14 @@ def run_ours(args):
         total_ms, launches, (kern_ms, kern_n) = timed(device_step, args.steps, args.warmup, profile=True)
         # end to end through the public API: host numpy in, host numpy out, every step
         e2e_ms, _, _ = timed(host_step, args.steps, max(3, args.warmup // 2))
+    exchange = "none (1 GPU)"
+    ranks_agree = None
+    if world > 1:
+        exchange = "peer memory (CUDA IPC, NVLink P2P loads in the merge-side kernel)" if getattr(opt, "_p2p", False) else "NCCL all_gather per iteration"
+        a_me, _, _ = opt(d_state, 10 ** 6, False)
+        a_all = torch.empty(world, *a_me.shape, device=dev)
+        dist.all_gather_into_tensor(a_all, a_me.contiguous())
+        ranks_agree = bool((a_all == a_all[0:1]).all().item())
     A = w.num_agents
     h2d = A * w.dS * 4
     d2h = (A * w.dU + A * w.dS + A) * 4
@@ -300,7 +308,8 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(w, {"precision": eff_prec, "l2": "flushed (256 MB write) before every timed step",
-                                      "parallelism": f"population sharded over {world} GPU(s)"}),
+                                      "parallelism": f"population sharded over {world} GPU(s)", "exchange": exchange,
+                                      "ranks_agree": ranks_agree}),
         "clocks": clocks.summary(),
         "e2e": {"value": 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "api": "MPCPolicy.act(numpy obs) -> numpy (action, next_obs, reward)"},

@@ -65,6 +65,8 @@ SIGNATURES = {
     "bbmpc_opt_iter_local": (_I, [_VP, _I, _VP, _VP]),
     "bbmpc_opt_iter_merge": (_I, [_VP, _I, _VP, _I, _VP]),
     "bbmpc_opt_finish": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
+    "bbmpc_opt_p2p_export": (_I, [_VP, _VP, C.POINTER(_VP)]),
+    "bbmpc_opt_p2p_connect": (_I, [_VP, _VP, C.POINTER(_VP)]),
     "bbmpc_opt_get_tensor": (_I64, [_VP, C.c_char_p, _VP, _I64, _VP]),
     "bbmpc_opt_set_sample_trace": (_I, [_VP, _VP, _I64]),
     "bbmpc_philox4x32_host": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

@@ -33,6 +33,13 @@ struct bbmpc_opt {
   float *d_m = nullptr, *d_sigma = nullptr, *d_C = nullptr, *d_B = nullptr, *d_D = nullptr, *d_ps = nullptr,
         *d_pc = nullptr, *d_z = nullptr, *d_BD = nullptr, *d_work = nullptr, *d_cma_w = nullptr;
   double cma_consts[16] = {0};
+  // peer-memory exchange: [2 parities][partial_floats] messages + one sequence flag (last 64 bytes)
+  float* p2p_buf = nullptr; size_t p2p_bytes = 0;
+  float** d_peer = nullptr;        // [world] device table of the ranks' exchange buffers (own entry = p2p_buf)
+  float* d_gather = nullptr;       // [world, partial_floats] local copy of the gathered messages
+  std::vector<void*> p2p_opened;   // cudaIpcOpenMemHandle mappings to close
+  bool p2p_on = false;
+  uint32_t p2p_seq = 0;            // exchanges published so far (monotonic over the handle's lifetime)
   // trace + pinned staging
   float* trace = nullptr; int64_t trace_floats = 0;
   float* h_pinned = nullptr;

@@ -459,6 +459,40 @@ __global__ void pso_seed_kernel(float* x, float* v, float* pbx, const float* gbx
   x[i] = pos; pbx[i] = pos; v[i] = vel;
 }
 
+// ---- peer-memory exchange (NVLink P2P).  Publish: the partial message is already in this rank's exchange
+// buffer; make it visible system-wide, then store the sequence number.  Gather: block g waits until rank g
+// has published `seq`, then copies its message into the local gather buffer with plain P2P loads.
+__global__ void p2p_publish_kernel(uint32_t* flag, uint32_t seq) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag), "r"(seq) : "memory");
+}
+__global__ void __launch_bounds__(256) p2p_gather_kernel(float* const* peers, float* gathered, int n_floats, size_t flag_off_floats,
+                                                         uint32_t seq, int parity) {
+  const int g = blockIdx.x;
+  const float* src_base = peers[g];
+  if (threadIdx.x == 0) {
+    const uint32_t* flag = reinterpret_cast<const uint32_t*>(src_base + flag_off_floats);
+    uint32_t seen = 0, spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+      if (seen < seq && ++spins > (1u << 26)) asm volatile("trap;");   // a peer died: abort instead of hanging
+    } while (seen < seq);
+  }
+  __syncthreads();
+  const float4* src = reinterpret_cast<const float4*>(src_base + static_cast<size_t>(parity) * n_floats);
+  float4* dst = reinterpret_cast<float4*>(gathered + static_cast<size_t>(g) * n_floats);
+  for (int i = threadIdx.x; i < n_floats / 4; i += blockDim.x) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + i) : "memory");
+    dst[i] = v;
+  }
+  for (int i = (n_floats / 4) * 4 + threadIdx.x; i < n_floats; i += blockDim.x) {
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(src_base + static_cast<size_t>(parity) * n_floats + i) : "memory");
+    gathered[static_cast<size_t>(g) * n_floats + i] = v;
+  }
+}
+
 inline int grid_for(int64_t n, int block) { return static_cast<int>((n + block - 1) / block); }
 
 }  // namespace
@@ -539,6 +573,7 @@ void bbmpc_opt_destroy(bbmpc_opt* o) {
   if (!o) return;
   cudaSetDevice(o->ctx->device);
   cudaDeviceSynchronize();
+  for (void* p : o->p2p_opened) cudaIpcCloseMemHandle(p);
   for (void* p : o->owned) cudaFree(p);
   if (o->h_pinned) cudaFreeHost(o->h_pinned);
   delete o;
@@ -813,10 +848,24 @@ int bbmpc_opt_finish(bbmpc_opt* o, int add_noise, float* action, float* next_sta
 int bbmpc_opt_call(bbmpc_opt* o, const float* state, int time_step, int add_noise, float* action, float* next_state,
                    float* reward, void* stream) {
   if (!o) return BBMPC_EINVAL;
-  if (o->world != 1) return opt_fail(o, BBMPC_ESTATE, "bbmpc_opt_call on a sharded optimizer: use begin/iter_local/iter_merge/finish");
+  if (o->world != 1 && !o->p2p_on)
+    return opt_fail(o, BBMPC_ESTATE, "bbmpc_opt_call on a sharded optimizer without a peer-memory exchange: use begin/iter_local/iter_merge/finish");
   if (int rc = bbmpc_opt_begin(o, state, time_step, stream)) return rc;
   const int n = bbmpc_opt_num_iterations(o);
   for (int it = 0; it < n; ++it) {
+    if (o->p2p_on) {
+      // publish this rank's message in its exchange buffer, pull the peers' over NVLink, merge locally
+      cudaStream_t st = static_cast<cudaStream_t>(stream);
+      const int nf = partial_floats(o);
+      const uint32_t seq = ++o->p2p_seq;
+      const int parity = static_cast<int>(seq & 1u);
+      if (int rc = bbmpc_opt_iter_local(o, it, o->p2p_buf + static_cast<size_t>(parity) * nf, stream)) return rc;
+      const size_t flag_off = 2 * static_cast<size_t>(nf);
+      p2p_publish_kernel<<<1, 1, 0, st>>>(reinterpret_cast<uint32_t*>(o->p2p_buf + flag_off), seq); BB_LAUNCH_CHECK(o->ctx);
+      p2p_gather_kernel<<<o->world, 256, 0, st>>>(o->d_peer, o->d_gather, nf, flag_off, seq, parity); BB_LAUNCH_CHECK(o->ctx);
+      if (int rc = bbmpc_opt_iter_merge(o, it, o->d_gather, o->world, stream)) return rc;
+      continue;
+    }
     if (int rc = bbmpc_opt_iter_local(o, it, nullptr, stream)) return rc;
     if (int rc = bbmpc_opt_iter_merge(o, it, nullptr, 1, stream)) return rc;
   }
@@ -842,6 +891,55 @@ int bbmpc_opt_call_host(bbmpc_opt* o, const float* state_host, int time_step, in
   std::memcpy(action_host, h_action, A * dU * sizeof(float));
   if (next_state_host) std::memcpy(next_state_host, h_next, A * dS * sizeof(float));
   if (reward_host) std::memcpy(reward_host, h_rew, A * sizeof(float));
+  return BBMPC_OK;
+}
+
+int bbmpc_opt_p2p_export(bbmpc_opt* o, void* handle_out_host, void** ptr_out_host) {
+  if (!o) return BBMPC_EINVAL;
+  bbmpc_ctx* ctx = o->ctx;
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!o->p2p_buf) {
+    const size_t nf = static_cast<size_t>(partial_floats(o));
+    o->p2p_bytes = (2 * nf + 16) * sizeof(float);
+    BB_CUDA(ctx, cudaMalloc(&o->p2p_buf, o->p2p_bytes));     // own allocation: an IPC handle exports the whole allocation
+    o->owned.push_back(o->p2p_buf);
+    BB_CUDA(ctx, cudaMemset(o->p2p_buf, 0, o->p2p_bytes));
+  }
+  if (handle_out_host) {
+    cudaIpcMemHandle_t h;
+    BB_CUDA(ctx, cudaIpcGetMemHandle(&h, o->p2p_buf));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle_out_host, &h, sizeof(h));
+  }
+  if (ptr_out_host) *ptr_out_host = o->p2p_buf;
+  return BBMPC_OK;
+}
+
+int bbmpc_opt_p2p_connect(bbmpc_opt* o, const void* handles_host, void* const* ptrs_host) {
+  if (!o) return BBMPC_EINVAL;
+  bbmpc_ctx* ctx = o->ctx;
+  if (!o->p2p_buf) return opt_fail(o, BBMPC_ESTATE, "p2p_connect before p2p_export");
+  if (!handles_host && !ptrs_host) return opt_fail(o, BBMPC_EINVAL, "p2p_connect needs IPC handles or device pointers");
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<float*> peers(o->world, nullptr);
+  for (int g = 0; g < o->world; ++g) {
+    if (g == o->rank) { peers[g] = o->p2p_buf; continue; }
+    if (ptrs_host && ptrs_host[g]) { peers[g] = static_cast<float*>(ptrs_host[g]); continue; }
+    if (!handles_host) return opt_fail(o, BBMPC_EINVAL, "p2p_connect: no handle or pointer for a peer");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const char*>(handles_host) + 64 * g, sizeof(h));
+    void* mapped = nullptr;
+    BB_CUDA(ctx, cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+    o->p2p_opened.push_back(mapped);
+    peers[g] = static_cast<float*>(mapped);
+  }
+  if (!o->d_peer) {
+    int rc = dalloc(o, &o->d_peer, o->world);
+    if (rc == BBMPC_OK) rc = dalloc(o, &o->d_gather, static_cast<size_t>(o->world) * partial_floats(o));
+    if (rc != BBMPC_OK) return rc;
+  }
+  BB_CUDA(ctx, cudaMemcpy(o->d_peer, peers.data(), o->world * sizeof(float*), cudaMemcpyHostToDevice));
+  o->p2p_on = true;
   return BBMPC_OK;
 }
 

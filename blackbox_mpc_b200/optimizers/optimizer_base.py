@@ -44,6 +44,7 @@ class OptimizerBase:
         self._rank, self._world, self._group = 0, 1, None
         self._gather_buf = None
         self._partial = None
+        self._p2p = False
 
     # -- hyper-parameters of the C handle; subclasses extend --------------------------------------
     def _config(self) -> dict:
@@ -93,6 +94,7 @@ class OptimizerBase:
             if self._world > 1:
                 e.check(e.lib.bbmpc_opt_set_shard(h, self._rank, self._world))
             self._alloc_io()
+            self._p2p = self._connect_p2p() if self._world > 1 else False
         return self._engine
 
     def _alloc_io(self):
@@ -105,6 +107,39 @@ class OptimizerBase:
         n = self._engine.lib.bbmpc_opt_partial_floats(self._handle)
         self._partial = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
         self._gather_buf = torch.empty(self._world, max(n, 1), dtype=torch.float32, device=dev)
+
+    def _connect_p2p(self) -> bool:
+        """Peer-memory exchange (bbmpc_opt_p2p_*): every rank exports its exchange buffer as a CUDA IPC
+        handle, the handles are all-gathered once, and from then on a sharded act() is ONE call into
+        libbbmpc — partial messages are pulled over NVLink inside the merge-side kernel instead of an NCCL
+        all_gather per iteration.  Needs all ranks on one node; BBMPC_P2P=0 keeps the all_gather path."""
+        import os
+        import torch.distributed as dist
+        if os.environ.get("BBMPC_P2P", "1") == "0" or not (dist.is_available() and dist.is_initialized()):
+            return False
+        if dist.get_backend(self._group) != "nccl":
+            return False
+        if int(os.environ.get("LOCAL_WORLD_SIZE", self._world)) != self._world:
+            return False                      # ranks on several nodes: IPC handles do not travel
+        e, lib = self._engine, self._engine.lib
+        ok = 1
+        try:
+            handle = (C.c_ubyte * 64)()
+            e.check(lib.bbmpc_opt_p2p_export(self._handle, handle, None))
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=e.device)
+        except Exception:
+            ok, mine = 0, torch.zeros(64, dtype=torch.uint8, device=e.device)
+        gathered = torch.empty(self._world * 64, dtype=torch.uint8, device=e.device)
+        dist.all_gather_into_tensor(gathered, mine, group=self._group)
+        if ok:
+            try:
+                buf = gathered.cpu().numpy().tobytes()
+                e.check(lib.bbmpc_opt_p2p_connect(self._handle, buf, None))
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=e.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._group)   # all ranks or none
+        return bool(flag.item())
 
     # -- population sharding (one process per GPU) ------------------------------------------------
     def shard(self, rank: int, world: int, group=None):
@@ -129,7 +164,7 @@ class OptimizerBase:
             raise ValueError(f"current_state must be [{self._num_agents}, {self._dim_S}]")
         action, nxt, rew = (torch.empty_like(self._d_action), torch.empty_like(self._d_next), torch.empty_like(self._d_reward))
         noise = 1 if bool(add_exploration_noise) else 0
-        if self._world == 1:
+        if self._world == 1 or self._p2p:
             e.check(lib.bbmpc_opt_call(h, _lib.ptr(state), int(time_step), noise, _lib.ptr(action), _lib.ptr(nxt), _lib.ptr(rew), st))
         else:
             e.check(lib.bbmpc_opt_begin(h, _lib.ptr(state), int(time_step), st))
@@ -143,7 +178,7 @@ class OptimizerBase:
     def call_host(self, observations: np.ndarray, time_step: int, add_exploration_noise: bool):
         """MPCPolicy.act's fast path: numpy [A,dS] in, numpy out, one synchronisation."""
         e = self._ensure_handle()
-        if self._world != 1:
+        if self._world != 1 and not self._p2p:
             a, n, r = self.__call__(torch.from_numpy(np.ascontiguousarray(observations, dtype=np.float32)), time_step, add_exploration_noise)
             return a.cpu().numpy(), n.cpu().numpy(), r.cpu().numpy()
         obs = np.ascontiguousarray(observations, dtype=np.float32)

@@ -167,6 +167,18 @@ int bbmpc_opt_iter_merge(bbmpc_opt* opt, int iter, const float* partials, int wo
 int bbmpc_opt_finish(bbmpc_opt* opt, int add_exploration_noise, float* action, float* next_state,
                      float* reward, void* stream);
 
+/* Peer-memory exchange (one process per GPU on one NVLink/NVSwitch box; new: the reference is single-device).
+ * Instead of an NCCL all_gather between iter_local and iter_merge, every rank publishes its partial message
+ * in a device buffer that the other ranks have mapped (CUDA IPC), and the merge side of each rank pulls the
+ * peers' messages over NVLink inside one kernel (flag wait + P2P loads).  Once connected, bbmpc_opt_call /
+ * bbmpc_opt_call_host run the whole sharded act() without returning to the host between iterations.
+ *   bbmpc_opt_p2p_export: allocates the exchange buffer and writes its 64-byte cudaIpcMemHandle_t to
+ *                         handle_out (host) and its device address to ptr_out (for same-process peers).
+ *   bbmpc_opt_p2p_connect: handles_host = world x 64 bytes (rank order) or NULL; ptrs_host = world device
+ *                         addresses (same-process peers / tests) or NULL.  Entry `rank` is ignored. */
+int bbmpc_opt_p2p_export(bbmpc_opt* opt, void* handle_out_host, void** ptr_out_host);
+int bbmpc_opt_p2p_connect(bbmpc_opt* opt, const void* handles_host, void* const* ptrs_host);
+
 /* Test/inspection hooks.  name: "mean" "variance" (CEM/PI2), "solution" (SPSA), "samples"
  * (last iteration's local samples [P_local,A,H,dU]), "returns" ([P_local,A], penalties applied),
  * "m" "sigma" "C" "B" "D" (diagonal) "p_sigma" "p_C" (CMA-ES), "x" "v" "pbest_x" "pbest_r" "gbest_x" (PSO).

@@ -152,3 +152,27 @@ def test_shard_invariance_single_gpu(cuda_device):
             torch.cuda.synchronize()
             assert torch.equal(o.get_tensor("mean").cpu(), ref_mean), f"world={world}"
             assert torch.equal(act.cpu(), ref_action.cpu())
+
+
+def test_peer_memory_exchange_single_rank(cuda_device):
+    """bbmpc_opt_p2p_export / _connect with world = 1 (the rank pulls its own message through the exchange
+    buffer): publish -> flag wait -> gather -> merge must reproduce the plain path bit for bit."""
+    import ctypes as C
+    w = workloads.make("C2", population_size=300, num_agents=2, bias_scale=0.1)
+    w.optimizer_args = dict(num_elite=16, alpha=0.25)
+    ref_policy = workloads.build_policy(w, precision="fp32")
+    ref_action, ref_next, _ = ref_policy._optimizer(torch.from_numpy(w.state), 0, False)
+    policy = workloads.build_policy(w, precision="fp32")
+    opt = policy._optimizer
+    e = opt._ensure_handle()
+    ptr = C.c_void_p()
+    handle = (C.c_ubyte * 64)()
+    e.check(e.lib.bbmpc_opt_p2p_export(opt._handle, handle, C.byref(ptr)))
+    assert ptr.value
+    ptrs = (C.c_void_p * 1)(ptr.value)
+    e.check(e.lib.bbmpc_opt_p2p_connect(opt._handle, None, ptrs))
+    for t in range(2):      # twice: sequence numbers / buffer parity advance across act() calls
+        action, nxt, _ = opt(torch.from_numpy(w.state), t, False)
+        torch.cuda.synchronize()
+    ref_action2, _, _ = ref_policy._optimizer(torch.from_numpy(w.state), 1, False)
+    assert torch.equal(action.cpu(), ref_action2.cpu())
