@@ -179,14 +179,15 @@ __global__ void penalty_kernel(const float* excess_sq, float* penalty, int64_t r
 // partial layout per agent: E records of (reward, global_p bits, seq[HU]).
 __global__ void __launch_bounds__(SEL_THREADS) topk_partial_kernel(const float* returns, const float* samples,
                                                                    float* partial, int P_local, int p0, int A,
-                                                                   int HU, int E) {
+                                                                   int HU, int E, int use_cache) {
   __shared__ int hist[256];
   __shared__ int misc[40];
   __shared__ uint32_t keys[SEL_MAX_K];
   __shared__ int idx[SEL_MAX_K];
+  extern __shared__ uint32_t topk_kcache[];   // P_local words when the launch provides them, else none
   const int a = blockIdx.x;
   const SelectScratch sc{hist, misc, keys, idx};
-  block_topk(returns + a, P_local, A, E, sc);
+  block_topk(returns + a, P_local, A, E, sc, use_cache ? topk_kcache : nullptr);
   const int rec = 2 + HU;
   float* out = partial + static_cast<size_t>(a) * E * rec;
   for (int i = threadIdx.x; i < E * rec; i += SEL_THREADS) {
@@ -503,7 +504,10 @@ void launch_penalty(const float* excess_sq, float* penalty, int64_t rows, int HU
 }
 void launch_topk_partial(const float* returns, const float* samples, float* partial, int P_local, int p0, int A, int HU, int E,
                          cudaStream_t st) {
-  topk_partial_kernel<<<A, SEL_THREADS, 0, st>>>(returns, samples, partial, P_local, p0, A, HU, E);
+  static bool attr_set = false;   // opt in to > 48 KB of shared memory once (per process; the attribute is per function)
+  if (!attr_set) { cudaFuncSetAttribute(topk_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr_set = true; }
+  const int use_cache = (P_local > 0 && P_local <= 16384) ? 1 : 0;   // 64 KB of dynamic shared memory at most
+  topk_partial_kernel<<<A, SEL_THREADS, use_cache ? P_local * sizeof(uint32_t) : 0, st>>>(returns, samples, partial, P_local, p0, A, HU, E, use_cache);
 }
 }  // namespace bbmpc
 
@@ -733,7 +737,7 @@ int bbmpc_opt_iter_local(bbmpc_opt* o, int iter, float* partial_out, void* strea
   }
   switch (c.kind) {
     case BBMPC_OPT_CEM:
-      topk_partial_kernel<<<A, SEL_THREADS, 0, st>>>(o->d_returns, o->d_samples, partial, o->P_local, o->p0, A, HU, c.num_elite);
+      launch_topk_partial(o->d_returns, o->d_samples, partial, o->P_local, o->p0, A, HU, c.num_elite, st);
       break;
     case BBMPC_OPT_PI2:
       pi2_partial_kernel<<<A, 1024, 0, st>>>(o->d_returns, o->d_samples, partial, o->P_local, A, HU, c.lamda);

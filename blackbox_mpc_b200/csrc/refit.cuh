@@ -80,10 +80,17 @@ __device__ inline void bitonic_sort_desc(uint32_t* keys, int* idx, int n2) {
 struct SelectScratch {
   int* hist; int* misc; uint32_t* out_keys; int* out_idx;
 };
+// `kcache` (nullable, n words of shared memory): the keys are read from global memory once and the five
+// further passes run out of shared memory.
 __device__ inline void block_topk(const float* __restrict__ vals, int n, int stride, int k,
-                                  const SelectScratch& sc) {
+                                  const SelectScratch& sc, uint32_t* kcache = nullptr) {
   const int tid = threadIdx.x;
   int k_eff = k < n ? k : n;
+  if (kcache) {
+    for (int i = tid; i < n; i += SEL_THREADS) kcache[i] = f2key(vals[static_cast<size_t>(i) * stride]);
+    __syncthreads();
+  }
+  auto key_at = [&](int i) -> uint32_t { return kcache ? kcache[i] : f2key(vals[static_cast<size_t>(i) * stride]); };
   for (int i = tid; i < SEL_MAX_K; i += SEL_THREADS) { sc.out_keys[i] = 0u; sc.out_idx[i] = 0x7FFFFFFF; }
   if (k_eff == 0) { __syncthreads(); return; }
   // --- radix select the k_eff-th largest key
@@ -94,7 +101,7 @@ __device__ inline void block_topk(const float* __restrict__ vals, int n, int str
     for (int i = tid; i < 256; i += SEL_THREADS) sc.hist[i] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += SEL_THREADS) {
-      const uint32_t ky = f2key(vals[static_cast<size_t>(i) * stride]);
+      const uint32_t ky = key_at(i);
       if ((ky & mask) == prefix) atomicAdd(&sc.hist[(ky >> shift) & 255], 1);
     }
     __syncthreads();
@@ -114,14 +121,14 @@ __device__ inline void block_topk(const float* __restrict__ vals, int n, int str
   if (tid == 0) sc.misc[36] = 0;
   __syncthreads();
   for (int i = tid; i < n; i += SEL_THREADS) {
-    const uint32_t ky = f2key(vals[static_cast<size_t>(i) * stride]);
+    const uint32_t ky = key_at(i);
     if (ky > T) { const int slot = atomicAdd(&sc.misc[36], 1); sc.out_keys[slot] = ky; sc.out_idx[slot] = i; }
   }
   // ties at the threshold: ordered scan so the lowest indices win
   int taken = 0;
   for (int base = 0; base < n && taken < need; base += SEL_THREADS) {
     const int i = base + tid;
-    const int flag = (i < n && f2key(vals[static_cast<size_t>(i) * stride]) == T) ? 1 : 0;
+    const int flag = (i < n && key_at(i) == T) ? 1 : 0;
     int total;
     const int rank = block_exclusive_scan(flag, sc.misc, total);
     if (flag && taken + rank < need) { sc.out_keys[n_greater + taken + rank] = T; sc.out_idx[n_greater + taken + rank] = i; }

@@ -218,9 +218,8 @@ __global__ void __launch_bounds__(TR* NG) step_simt_kernel(const SimtParams p) {
 }
 
 // Few-row variant of step_simt_kernel for the optimizer tail (optimizers/optimizer_base.py:91-94:
-// A rows) and small predict/forward calls.  One CTA per (row, ensemble member), thread = output
-// feature, so the serial K loop of a layer is spread over up to 256 coalesced weight streams
-// instead of one lane per row.  Same fp32 arithmetic and summation order as dense_layer().  The
+// A rows) and small predict/forward calls.  One CTA per (row, ensemble member); a layer's K axis is split
+// over the warps and its features over the lanes (fp32 FMA, partial sums added in warp order).  The
 // last CTA to finish a row (arrival counter) sums the members in member order and applies
 // process_output + reward.
 constexpr int STEP_THREADS = 256;
@@ -249,15 +248,40 @@ __global__ void __launch_bounds__(STEP_THREADS) step_mlp_kernel(const SimtParams
     in[k] = v;
   }
   __syncthreads();
+  // K is split over the 8 warps (contiguous ranges), a lane owns output features lane, lane+32, ...: every
+  // weight is read exactly once, coalesced, and all loads of a warp are independent (the former one-thread-
+  // per-feature loop was a chain of ~K/8 dependent DRAM round trips per layer: 286 us for the C4 ensemble).
+  // The warps' partial sums are added in warp order, then bias and activation.
+  float* part = smem_f + 2 * m.max_width;   // [STEP_WARPS][max_width]
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr int STEP_WARPS = STEP_THREADS / 32;
   for (int l = 0; l < m.n_layers; ++l) {
     const LayerDev& L = m.layer[l];
     const bool last = (l == m.n_layers - 1);
     const float* __restrict__ W = m.w32 + L.w_off + mm * m.w_member_stride;
     const float* __restrict__ bias = m.w32 + L.b_off + mm * m.w_member_stride;
+    const int kc = (L.K + STEP_WARPS - 1) / STEP_WARPS;
+    const int k0 = warp * kc, k1 = (k0 + kc < L.K) ? k0 + kc : L.K;
+    for (int f0 = 0; f0 < L.N; f0 += 256) {          // 8 features per lane per sweep
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+      for (int k = k0; k < k1; ++k) {
+        const float x = in[k];
+        const float* __restrict__ wr = W + static_cast<size_t>(k) * L.ldw + f0 + lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (f0 + lane + 32 * j < L.N) acc[j] = fmaf(x, __ldg(wr + 32 * j), acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (f0 + lane + 32 * j < L.N) part[warp * m.max_width + f0 + lane + 32 * j] = acc[j];
+    }
+    __syncthreads();
     for (int f = tid; f < L.N; f += STEP_THREADS) {
-      float acc = 0.0f;
-#pragma unroll 8
-      for (int k = 0; k < L.K; ++k) acc = fmaf(in[k], __ldg(W + static_cast<size_t>(k) * L.ldw + f), acc);
+      float acc = part[f];
+#pragma unroll
+      for (int w2 = 1; w2 < STEP_WARPS; ++w2) acc = __fadd_rn(acc, part[w2 * m.max_width + f]);
       const float v = act_exact(__fadd_rn(acc, __ldg(bias + f)), L.act);
       if (last) scratch[(static_cast<size_t>(b) * m.n_members + mm) * dS + f] = v;
       else out[f] = v;
@@ -339,7 +363,7 @@ int launch_step_simt(bbmpc_ctx* ctx, const StepIO& io, cudaStream_t st) {
       BB_CUDA(ctx, cudaMalloc(&ctx->step_counters, sizeof(unsigned) * STEP_MAX_ROWS));
       BB_CUDA(ctx, cudaMemset(ctx->step_counters, 0, sizeof(unsigned) * STEP_MAX_ROWS));
     }
-    const size_t sb = sizeof(float) * 2 * static_cast<size_t>(p.mlp.max_width > MAX_DS ? p.mlp.max_width : MAX_DS);
+    const size_t sb = sizeof(float) * (2 + STEP_THREADS / 32) * static_cast<size_t>(p.mlp.max_width > MAX_DS ? p.mlp.max_width : MAX_DS);
     step_mlp_kernel<<<dim3(io.B, p.mlp.n_members), STEP_THREADS, sb, st>>>(p, ctx->step_scratch, ctx->step_counters);
     BB_LAUNCH_CHECK(ctx);
     return BBMPC_OK;
