@@ -128,3 +128,42 @@ def test_member_parallel_matches_single_cta(cuda_device, monkeypatch, P, A):
     monkeypatch.delenv("BBMPC_NO_GROUPS")
     assert np.isfinite(r_group).all()
     helpers.compare_returns(r_group, r_single, max_jump_frac=0.02, **TOL["bf16x3"])
+
+
+def _custom_workload(layers, acts, n_members, dS, dU, P, A, H, seed):
+    """A halfcheetah-style (dS >= 18) or pendulum-style workload with arbitrary MLP shape."""
+    base = workloads.make("C4" if dS >= 18 else "C2", population_size=P, planning_horizon=H, num_agents=A, seed=seed, bias_scale=0.1)
+    members = [workloads.glorot_mlp(layers, seed + 10 * m, 0.1) for m in range(n_members)]
+    base.layers, base.activations = layers, acts
+    base.weights, base.biases = [m[0] for m in members], [m[1] for m in members]
+    base.dS, base.dU = dS, dU
+    base.lb, base.ub = -np.ones(dU, np.float32), np.ones(dU, np.float32)
+    base.stats = workloads._stats(dS, dU, seed)
+    g = torch.Generator().manual_seed(77 + seed)
+    base.state = (torch.randn(A, dS, generator=g) * 0.5).numpy().astype(np.float32)
+    if dS < 18:
+        base.state[:, :2] /= np.linalg.norm(base.state[:, :2], axis=1, keepdims=True)
+    return base
+
+
+@pytest.mark.parametrize("layers,acts,n_members,dS,dU,P,A", [
+    ([4, 16, 3], ["tanh", None], 2, 3, 1, 200, 1),                          # tiny ensemble, pendulum-style reward
+    ([26, 100, 100, 20], ["tanh", "relu", None], 3, 20, 6, 300, 2),        # mixed activations, 3 members, 2 agents
+    ([26, 200, 20], ["sigmoid", None], 1, 20, 6, 150, 1),                   # one hidden layer, sigmoid
+    ([42, 64, 64, 64, 64, 30], ["tanh"] * 4 + [None], 8, 30, 12, 257, 1),  # 8 members, dS=30, dU=12, 5 layers
+    ([32, 200, 200, 20], ["tanh", "tanh", None], 2, 20, 12, 129, 1),       # widest layers the TMEM budget admits with a 16-slot action block
+    ([26, 20], [None], 1, 20, 6, 100, 1),                                   # linear single layer
+])
+def test_rollout_shapes_against_oracle(cuda_device, layers, acts, n_members, dS, dU, P, A):
+    """Tensor-core path over model shapes the BASELINE configs do not touch: member counts (member-parallel
+    groups of 2..8 CTAs), layer counts, widths with ragged tail chunks, activation mixes, state/action widths
+    that select the other kernel instantiations."""
+    H = 12
+    w = _custom_workload(layers, acts, n_members, dS, dU, P, A, H, seed=3)
+    _, ev = _policy_and_eval(w, "bf16x3")
+    assert ev.engine().effective_precision == "bf16x3"
+    actions = helpers.random_actions(w, P, seed=5)
+    state = torch.from_numpy(w.state)
+    got = ev(state, actions, 0).cpu().numpy()
+    ref = helpers.oracle_evaluator(w, torch.float64)(state.double(), actions.double(), 0).numpy()
+    helpers.compare_returns(got, ref, max_jump_frac=0.05, **TOL["bf16x3"])
