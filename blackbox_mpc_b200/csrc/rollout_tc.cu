@@ -97,7 +97,7 @@ __host__ __device__ inline TcSmemLayout tc_layout(int stage_bytes, int n_stages,
   L.bars = off;   off += TC_NUM_BARS * 8;
   off = (off + 15u) & ~15u;
   L.tmem_slot = off; off += 16;
-  L.stats = off;  off += (4 * MAX_DS + 2 * MAX_DU) * 4;
+  L.stats = off;  off += (4 * MAX_DS + 2 * MAX_DU + 3 * 64) * 4;   // + layer-0 operand tables (mean / 1/den / add per K position)
   L.conv = off;   off += MAX_LAYERS * (32 + 256);   // per hidden layer: 8 ints + mask/add vectors of its 2 trailing chunks
   L.total = off;
   return L;
@@ -312,6 +312,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
   float* st_den_t = st_mean_t + MAX_DS;
   float* st_mean_a = st_den_t + MAX_DS;
   float* st_rden_a = st_mean_a + MAX_DU;
+  float* xt_mean = st_rden_a + MAX_DU;     // per K position of the layer-0 operand: x = (src - mean) * rden + add
+  float* xt_rden = xt_mean + 64;
+  float* xt_add = xt_rden + 64;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const MlpDev& M = p.mlp;
@@ -329,12 +332,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
     st_mean_s[i] = in ? p.norm.mean_s[i] : 0.0f;
     st_rden_s[i] = in ? __frcp_rn(p.norm.den_s[i]) : 1.0f;
     st_mean_t[i] = in ? p.norm.mean_t[i] : 0.0f;
-    st_den_t[i] = in ? p.norm.den_t[i] : 1.0f;
+    st_den_t[i] = in ? p.norm.den_t[i] : (i < p.dS ? 1.0f : 0.0f);
   }
   for (int i = tid; i < MAX_DU; i += TC_THREADS) {
     const bool in = norm_on && i < p.dU;
     st_mean_a[i] = in ? p.norm.mean_a[i] : 0.0f;
     st_rden_a[i] = in ? __frcp_rn(p.norm.den_a[i]) : 1.0f;
+  }
+  for (int k = tid; k < 64; k += TC_THREADS) {   // operand layout: [actions (DU_T slots) | state | 1 1 1 | 0 ...]
+    float mean = 0.0f, rden = 0.0f, add = 0.0f;
+    if (k < DU_T) {
+      if (k < p.dU) { mean = norm_on ? p.norm.mean_a[k] : 0.0f; rden = norm_on ? __frcp_rn(p.norm.den_a[k]) : 1.0f; }
+    } else {
+      const int i = k - DU_T;
+      if (i < p.dS) { mean = norm_on ? p.norm.mean_s[i] : 0.0f; rden = norm_on ? __frcp_rn(p.norm.den_s[i]) : 1.0f; }
+      else if (i < p.dS + BIAS_COLS) add = 1.0f;
+    }
+    xt_mean[k] = mean; xt_rden[k] = rden; xt_add[k] = add;
   }
   if (tid == 0) {
     for (int s = 0; s < p.n_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -531,26 +545,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
 #pragma unroll
         for (int c = 0; c < KP0_T; ++c) {
           if (c < kp0_chunks) {
-            float x[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int k = 16 * c + j;
-              float v;
-              if (k < DU_T) {
-                v = (k < p.dU) ? __fmul_rn(__fsub_rn(a[k < DU_T ? k : 0], st_mean_a[k < DU_T ? k : 0]), st_rden_a[k < DU_T ? k : 0]) : 0.0f;
-              } else {
-                const int i = k - DU_T;
-                const float one_or_zero = (i >= p.dS && i < p.dS + BIAS_COLS) ? 1.0f : 0.0f;
-                if (i < DS_T)
-                  v = (i < p.dS) ? __fmul_rn(__fsub_rn(s[i < DS_T ? i : 0], st_mean_s[i < DS_T ? i : 0]), st_rden_s[i < DS_T ? i : 0]) : one_or_zero;
-                else
-                  v = one_or_zero;
-              }
-              x[j] = v;
-            }
             uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) split_bf16x2(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
+            for (int j4 = 0; j4 < 16; j4 += 4) {
+              const float4 mn = *reinterpret_cast<const float4*>(xt_mean + 16 * c + j4);
+              const float4 rd = *reinterpret_cast<const float4*>(xt_rden + 16 * c + j4);
+              const float4 ad = *reinterpret_cast<const float4*>(xt_add + 16 * c + j4);
+              float src[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int k = 16 * c + j4 + j;        // compile-time position -> register of a[] / s[]
+                src[j] = (k < DU_T) ? a[k < DU_T ? k : 0] : ((k - DU_T < DS_T) ? s[(k - DU_T < DS_T && k >= DU_T) ? k - DU_T : 0] : 0.0f);
+              }
+              const float x0 = fmaf(__fsub_rn(src[0], mn.x), rd.x, ad.x), x1 = fmaf(__fsub_rn(src[1], mn.y), rd.y, ad.y);
+              const float x2 = fmaf(__fsub_rn(src[2], mn.z), rd.z, ad.z), x3 = fmaf(__fsub_rn(src[3], mn.w), rd.w, ad.w);
+              split_bf16x2_packed(pk2(x0, x1), hi[j4 / 2], lo[j4 / 2]);
+              split_bf16x2_packed(pk2(x2, x3), hi[j4 / 2 + 1], lo[j4 / 2 + 1]);
+            }
             tmem_st8(tm + p.col_x + 16 * c, hi);
             if (p.passes == 3) tmem_st8(tm + p.col_x + 16 * c + 8, lo);
           }
@@ -613,14 +624,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
               mbar_wait(bar_xs, static_cast<uint32_t>(gstep & 1), dbgp, 0x7000000u);
               tr.rec(0x36u);
               const float4* xs = reinterpret_cast<const float4*>(smem + lay.xs) + row_in_tile * (DS_T / 4);
-#pragma unroll 1
-              for (int m2 = 0; m2 < nM; ++m2) {
+              // member order, all loads of a column group in flight together (group mode has nM <= 8)
 #pragma unroll
-                for (int c = 0; c < DS_T / 4; ++c) {
-                  const float4 v = xs[m2 * (TILE_ROWS * DS_T / 4) + c];
-                  acc[4 * c] = __fadd_rn(acc[4 * c], v.x); acc[4 * c + 1] = __fadd_rn(acc[4 * c + 1], v.y);
-                  acc[4 * c + 2] = __fadd_rn(acc[4 * c + 2], v.z); acc[4 * c + 3] = __fadd_rn(acc[4 * c + 3], v.w);
-                }
+              for (int c = 0; c < DS_T / 4; ++c) {
+                float4 v[8];
+#pragma unroll
+                for (int m2 = 0; m2 < 8; ++m2)
+                  if (m2 < nM) v[m2] = xs[m2 * (TILE_ROWS * DS_T / 4) + c];
+#pragma unroll
+                for (int m2 = 0; m2 < 8; ++m2)
+                  if (m2 < nM) {
+                    acc[4 * c] = __fadd_rn(acc[4 * c], v[m2].x); acc[4 * c + 1] = __fadd_rn(acc[4 * c + 1], v[m2].y);
+                    acc[4 * c + 2] = __fadd_rn(acc[4 * c + 2], v[m2].z); acc[4 * c + 3] = __fadd_rn(acc[4 * c + 3], v[m2].w);
+                  }
               }
               // every state thread is done with the staging area before the next step's copies may land:
               // guaranteed by the bar.sync at the top of the next exchange (the copies are issued after it).
@@ -653,8 +669,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
           for (int i = 0; i < DS_T; ++i) {
             float y = __uint_as_float(r[i / 8][i % 8]);
             if (nM > 1) y = __fmul_rn(y, inv_members);
-            const float dlt = norm_on ? __fadd_rn(st_mean_t[i], __fmul_rn(y, st_den_t[i])) : y;
-            s2[i] = (i < p.dS) ? __fadd_rn(dlt, s[i]) : 0.0f;
+            s2[i] = __fadd_rn(fmaf(y, st_den_t[i], st_mean_t[i]), s[i]);   // tables hold (0, 1) without normalisation, (0, 0) beyond dS
           }
         }
         // all of this thread's TMEM reads of D_out are complete (wait_ld) before the next arrive.
@@ -752,7 +767,7 @@ static int launch_t(bbmpc_ctx* ctx, const TcParams& p, int grid, size_t smem_byt
   // all hidden layers tanh (every reference tutorial): specialised kernel without the per-layer switch
   bool all_tanh = !(p.xflags & 2);
   for (int l = 0; l + 1 < p.mlp.n_layers; ++l) all_tanh = all_tanh && p.mlp.layer[l].act == BBMPC_ACT_TANH;
-  auto kern = (p.trace || p.dbg) ? rollout_tc_kernel<DS_T, DU_T, true, -1>
+  auto kern = (p.trace || p.dbg) ? (all_tanh ? rollout_tc_kernel<DS_T, DU_T, true, BBMPC_ACT_TANH> : rollout_tc_kernel<DS_T, DU_T, true, -1>)
                                  : (all_tanh ? rollout_tc_kernel<DS_T, DU_T, false, BBMPC_ACT_TANH> : rollout_tc_kernel<DS_T, DU_T, false, -1>);
   BB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
   if (p.group_mode) {
