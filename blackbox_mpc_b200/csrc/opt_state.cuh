@@ -24,6 +24,7 @@ struct bbmpc_opt {
   float* d_prev = nullptr;        // persistent "previous solution" / current parameters [A,H,dU]
   float* d_var0 = nullptr;        // persistent solution variance [A,H,dU]
   float* d_partial = nullptr;     // [partial_floats]
+  float* d_pi2_scratch = nullptr; // PI2: per-slice weighted sums [A, 64, H*dU]
   float* d_action = nullptr;      // [A,dU]
   float* d_next = nullptr;        // [A,dS]
   float* d_reward = nullptr;      // [A]

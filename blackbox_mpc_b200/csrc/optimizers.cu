@@ -284,15 +284,40 @@ __global__ void __launch_bounds__(1024) pi2_partial_kernel(const float* returns,
   __syncthreads();
   float* out = partial + static_cast<size_t>(a) * (2 + HU);
   if (tid == 0) { out[0] = mx; out[1] = s_sum; }
-  // weighted sums: warp w handles elements e = w, w+32, ...; lanes stride the population
-  for (int e = warp; e < HU; e += 32) {
+}
+// weighted sums sum_p e_p x[p, a, :]: block (a, b) takes a contiguous slice of the population, thread = element
+// (coalesced sample reads, the slice's weights staged in shared memory), slices are added in slice order by
+// pi2_wsum_reduce_kernel: deterministic, and no longer one CTA striding 3.6 MB with 32-byte-sector reads.
+constexpr int PI2_SLICES = 64, PI2_ROWS = 128;
+__global__ void __launch_bounds__(256) pi2_wsum_kernel(const float* __restrict__ returns, const float* __restrict__ samples,
+                                                       const float* __restrict__ partial, float* __restrict__ scratch,
+                                                       int P_local, int A, int HU, float lamda) {
+  __shared__ float wgt[PI2_ROWS];
+  const int a = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const float mx = partial[static_cast<size_t>(a) * (2 + HU)];
+  const float inv_l = __fdiv_rn(1.0f, lamda);
+  const int per = (P_local + PI2_SLICES - 1) / PI2_SLICES;
+  const int p_begin = b * per, p_end = (p_begin + per < P_local) ? p_begin + per : P_local;
+  for (int e0 = 0; e0 < HU; e0 += 256) {
+    const int e = e0 + tid;
     float acc = 0.0f;
-    for (int p = lane; p < P_local; p += 32) {
-      const float wgt = expf(-inv_l * ((-returns[p * A + a]) - (-mx)));
-      acc = fmaf(wgt, samples[(static_cast<size_t>(p) * A + a) * HU + e], acc);
+    for (int p0 = p_begin; p0 < p_end; p0 += PI2_ROWS) {
+      const int n = (p_end - p0 < PI2_ROWS) ? p_end - p0 : PI2_ROWS;
+      __syncthreads();
+      if (tid < n) wgt[tid] = expf(-inv_l * ((-returns[static_cast<size_t>(p0 + tid) * A + a]) - (-mx)));
+      __syncthreads();
+      if (e < HU)
+        for (int i = 0; i < n; ++i) acc = fmaf(wgt[i], samples[(static_cast<size_t>(p0 + i) * A + a) * HU + e], acc);
     }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) out[2 + e] = acc;
+    if (e < HU) scratch[(static_cast<size_t>(a) * PI2_SLICES + b) * HU + e] = acc;
+  }
+}
+__global__ void pi2_wsum_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ partial, int A, int HU) {
+  const int a = blockIdx.x;
+  for (int e = threadIdx.x; e < HU; e += blockDim.x) {
+    float acc = 0.0f;
+    for (int b = 0; b < PI2_SLICES; ++b) acc = __fadd_rn(acc, scratch[(static_cast<size_t>(a) * PI2_SLICES + b) * HU + e]);
+    partial[static_cast<size_t>(a) * (2 + HU) + 2 + e] = acc;
   }
 }
 // PI2 merge: log-sum-exp combination of the ranks' partials -> new mean (pi2.py:80-87)
@@ -606,6 +631,7 @@ static int set_shard(bbmpc_opt* o, int rank, int world) {
   if (o->cfg.kind == BBMPC_OPT_PI2 || o->cfg.kind == BBMPC_OPT_SPSA || o->cfg.kind == BBMPC_OPT_PSO)
     A_(dalloc(o, &o->d_work, rows * o->HU));
   if (o->cfg.kind == BBMPC_OPT_CMAES) A_(cmaes_set_shard(o));
+  if (o->cfg.kind == BBMPC_OPT_PI2 && !o->d_pi2_scratch) A_(dalloc(o, &o->d_pi2_scratch, static_cast<size_t>(A) * PI2_SLICES * o->HU));
   if (o->cfg.kind == BBMPC_OPT_PSO) {
     A_(dalloc(o, &o->d_v, rows * o->HU)); A_(dalloc(o, &o->d_pbx, rows * o->HU)); A_(dalloc(o, &o->d_pbr, rows));
     if (rc == BBMPC_OK) {
@@ -740,7 +766,9 @@ int bbmpc_opt_iter_local(bbmpc_opt* o, int iter, float* partial_out, void* strea
       launch_topk_partial(o->d_returns, o->d_samples, partial, o->P_local, o->p0, A, HU, c.num_elite, st);
       break;
     case BBMPC_OPT_PI2:
-      pi2_partial_kernel<<<A, 1024, 0, st>>>(o->d_returns, o->d_samples, partial, o->P_local, A, HU, c.lamda);
+      pi2_partial_kernel<<<A, 1024, 0, st>>>(o->d_returns, o->d_samples, partial, o->P_local, A, HU, c.lamda); BB_LAUNCH_CHECK(ctx);
+      pi2_wsum_kernel<<<dim3(A, PI2_SLICES), 256, 0, st>>>(o->d_returns, o->d_samples, partial, o->d_pi2_scratch, o->P_local, A, HU, c.lamda); BB_LAUNCH_CHECK(ctx);
+      pi2_wsum_reduce_kernel<<<A, 256, 0, st>>>(o->d_pi2_scratch, partial, A, HU);
       break;
     case BBMPC_OPT_RANDOM_SEARCH:
       argmax_partial_kernel<<<A, 1024, 0, st>>>(o->d_returns, o->d_samples, partial, o->P_local, o->p0, A, HU);
