@@ -8,25 +8,30 @@
 // both operands into bf16 hi + lo and issuing three MMAs per K-chunk (hi*hi, lo*hi, hi*lo;
 // the dropped lo*lo term is O(2^-18)); BBMPC_PREC_BF16 issues only hi*hi.
 //
-//   warp 0      producer: streams weight chunks L2 -> SMEM ring with cp.async.bulk + mbarrier tx
-//   warp 1      MMA issuer (one elected lane): tcgen05.mma A-from-TMEM, tcgen05.commit
-//   warps 2..9  epilogue: thread <-> (trajectory, column half).  tcgen05.ld accumulator ->
-//               activation -> bf16 hi/lo split -> tcgen05.st as the next layer's A operand.
-//               Trajectory state, action and return live in registers for all H steps.
+//   warp 0       producer: streams the weight image L2 -> SMEM ring in groups of K-chunks
+//                (cp.async.bulk + mbarrier tx bytes; one full/empty handshake per group)
+//   warp 1       MMA issuer (one elected lane): tcgen05.mma A-from-TMEM, tcgen05.commit
+//   warp 2       owns the TMEM allocation; warp 3 idle (warpgroup padding)
+//   warps 4..7   state warps, one per TMEM lane quarter: trajectory state, action and return of 32 rows in
+//                registers for all H steps; build the layer-0 operand, consume the output accumulator
+//   warps 8..    conversion warps, EPI_SUB per lane quarter: tcgen05.ld accumulator chunk -> activation ->
+//                bf16 hi/lo split -> tcgen05.st as the next layer's A operand
 //
 // Layer pipeline.  The accumulator of layer l is converted IN PLACE, 16 columns at a time, into
-// the A operand of layer l+1 (columns [16c,16c+8) = hi, [16c+8,16c+16) = lo of K-chunk c), and
-// every converted chunk is published on its own mbarrier.  The MMA issuer consumes chunks as
-// they appear and accumulates layer l+1 into the other of two TMEM buffers, so the tensor pipe
-// works on layer l+1 while the epilogue warps are still converting layer l.  For an ensemble the
-// first layer of member m+1 (whose input X is already in TMEM) is issued ahead of the output
-// layer of member m, which keeps the epilogue fed across the member boundary.
+// the A operand of layer l+1 (columns [16c,16c+8) = hi, [16c+8,16c+16) = lo of K-chunk c); converted
+// chunks are published per UNIT (pair of chunks) on the unit's mbarrier.  The MMA issuer consumes units as
+// they appear (probing the next unit's barrier before it issues the current unit's MMAs) and accumulates
+// layer l+1 into the other of two TMEM buffers, so the tensor pipe works on layer l+1 while layer l is
+// still being converted.  One CTA per tile (single models): the first layer of member m+1 is issued ahead
+// of the output layer of member m and all members' output layers accumulate into one TMEM tile.
+// Member-parallel mode (ensembles): the n_members CTAs of a group share a tile, one member each, and
+// exchange their raw outputs through L2 once per horizon step (see the state-warp code).
 //
 // Activations never touch shared or global memory; HBM traffic is the action read
 // (H*dU floats per trajectory) and the 4-byte return.  Bias is folded into the GEMM: the A
-// operand carries three ones-columns that meet three bf16 bias rows of the weight image.
-// The ensemble mean is folded too: every member's output layer accumulates into the same TMEM
-// tile (accumulate flag), the epilogue divides by n_members.
+// operand carries three ones-columns that meet three bf16 bias rows of the weight image; hidden tanh
+// layers carry 2 log2(e) in their weights so the activation starts at ex2.
+// DESIGN.md section 4.1 has the measurements behind each of these choices.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
