@@ -1,4 +1,4 @@
-"""SystemDynamicsHandler — inference half.
+"""SystemDynamicsHandler.
 
 Mirrors blackbox_mpc/dynamics_handlers/system_dynamics_handler.py:7-161: constructor signature,
 process_input (:97-126), process_output (:128-161), normalisation statistics (six fp32 vectors,
@@ -6,7 +6,9 @@ process_input (:97-126), process_output (:128-161), normalisation statistics (si
 re-stages weights/statistics into libbbmpc whenever the dynamics function's version changes (the
 handler is shared with the trainer in the reference, utils/iterative_mpc.py:147-157).
 
-The training half (train / _training_algorithm / save, :163-349) is out of scope (SURVEY §2 #3')."""
+The training half (train, :163-243) lives in training.py (PyTorch stock ops: it is not
+on the act() path); train() appends the trajectories, fits the model(s) in place and bumps the versions
+so that the next act() re-stages weights and statistics."""
 from __future__ import annotations
 
 import ctypes as C
@@ -18,6 +20,7 @@ import torch
 
 from .. import _lib
 from ..engine import Engine
+from . import training
 
 _STAT_NAMES = ("mean_states", "std_states", "mean_actions", "std_actions", "mean_targets", "std_targets")
 
@@ -65,9 +68,22 @@ class SystemDynamicsHandler:
         self._stats = None          # six CUDA tensors once set
         self._stats_version = 0
         self._staged = (None, -1, -1)   # (id(dynamics_function), its version, stats version)
-        if saved_model_dir is not None and self._is_normalized and not self._is_true_model:
-            # same six file names as the reference (:84-95)
-            self.set_normalization(*[np.load(os.path.join(saved_model_dir, n + ".npy")) for n in _STAT_NAMES])
+        # training state (:60-76)
+        self._model_training_in = np.zeros((0, self._dim_S + self._dim_U), np.float32)
+        self._model_training_out = np.zeros((0, self._dim_S), np.float32)
+        self._model_validation_in = np.zeros((0, self._dim_S + self._dim_U), np.float32)
+        self._model_validation_out = np.zeros((0, self._dim_S), np.float32)
+        self._first_time, self._training_iter, self._refining_model_iter = True, 0, 0
+        self._rng = np.random.default_rng(seed)
+        self._torch_gen = torch.Generator().manual_seed(seed)
+        self.last_training_loss = self.last_validation_loss = None
+        if saved_model_dir is not None and not self._is_true_model:
+            if self._is_normalized:   # same six file names as the reference (:84-95)
+                self.set_normalization(*[np.load(os.path.join(saved_model_dir, n + ".npy")) for n in _STAT_NAMES])
+            saved = training.load_weights(saved_model_dir)
+            if saved is not None and dynamics_function is not None and hasattr(dynamics_function, "members"):
+                for member, (ws, bs) in zip(dynamics_function.members(), saved):
+                    member.set_weights(ws, bs)
 
     # -- statistics ---------------------------------------------------------------------------
     def set_normalization(self, mean_states, std_states, mean_actions, std_actions, mean_targets, std_targets):
@@ -112,5 +128,52 @@ class SystemDynamicsHandler:
             return raw_output + inputs_states
         return (self._mean_targets + raw_output * (self._std_targets + 1e-7)) + inputs_states
 
-    def train(self, *args, **kwargs):
-        raise NotImplementedError("dynamics training is outside the B200 hot path (SURVEY §8f-2)")
+    def get_dynamics_function(self):
+        return self._dynamics_function
+
+    # -- training half (:163-243) ---------------------------------------------------------------
+    def train(self, observations_trajectories, actions_trajectories, rewards_trajectories, validation_split=0.2,
+              batch_size=128, learning_rate=1e-3, epochs=30, nn_optimizer=None):
+        """Appends the trajectories to the dataset, (re)computes the statistics the first time, fits every
+        member of the dynamics function (Adam + loss_fn, default MSE) and saves `saved_model_<k>/` every
+        `save_model_frequency` calls.  `nn_optimizer` is accepted for signature compatibility (Adam is used)."""
+        if self._is_true_model:
+            raise Exception("a true model has nothing to train")
+        f = self._dynamics_function
+        if f is None or not hasattr(f, "members"):
+            raise TypeError("train() needs a DeterministicMLP / EnsembleMLP dynamics_function")
+        new_in, new_out = training.trajectories_to_samples(observations_trajectories, actions_trajectories, self._dim_S, self._dim_U)
+        tr_in, tr_out, va_in, va_out = training.split_train_validation(new_in, new_out, validation_split, self._rng)
+        self._model_training_in = np.concatenate([self._model_training_in, tr_in], 0)
+        self._model_training_out = np.concatenate([self._model_training_out, tr_out], 0)
+        self._model_validation_in = np.concatenate([self._model_validation_in, va_in], 0)
+        self._model_validation_out = np.concatenate([self._model_validation_out, va_out], 0)
+        if self._first_time:
+            if self._is_normalized:
+                self.set_normalization(*training.normalization_stats(self._model_training_in, self._model_training_out, self._dim_S))
+            self._first_time = False
+        if self._is_normalized:
+            stats = [t.cpu().numpy() for t in self._stats]
+            train_xy = training.normalize(self._model_training_in, self._model_training_out, stats, self._dim_S)
+            val_xy = training.normalize(self._model_validation_in, self._model_validation_out, stats, self._dim_S)
+        else:   # the reference normalises unconditionally and crashes here (SURVEY §9); raw data is the obvious intent
+            stats = None
+            train_xy = (self._model_training_in, self._model_training_out)
+            val_xy = (self._model_validation_in, self._model_validation_out)
+
+        def log_epoch(ep, _tr, va):
+            if self._tf_writer is not None and hasattr(self._tf_writer, "add_scalar"):
+                self._tf_writer.add_scalar("system_model_val/loss", va, self._refining_model_iter * epochs + ep)
+
+        losses = []
+        for member in f.members():
+            losses.append(training.fit_mlp(member.weights, member.biases, member.activation_ids, train_xy, val_xy, epochs=epochs,
+                                           learning_rate=learning_rate, batch_size=batch_size, loss_fn=member.loss_fn,
+                                           generator=self._torch_gen, on_epoch=log_epoch))
+            member.mark_dirty()
+        self.last_training_loss, self.last_validation_loss = losses[0]
+        self._refining_model_iter += 1
+        self._training_iter += 1
+        if self._training_iter % self._save_model_frequency == 0 and self._log_dir is not None:
+            training.save_model(os.path.join(self._log_dir, f"saved_model_{self._refining_model_iter}"),
+                                [m.weights for m in f.members()], [m.biases for m in f.members()], stats)
