@@ -72,3 +72,38 @@ def test_train_then_act_and_reload(cuda_device, tmp_path):
     ev2 = DeterministicTrajectoryEvaluator(reward_function=pendulum.pendulum_reward_function, system_dynamics_handler=handler2)
     st, ac = torch.from_numpy(s0[None]), torch.from_numpy(action[None])
     np.testing.assert_array_equal(ev1.predict_next_state(st, ac).cpu().numpy(), ev2.predict_next_state(st, ac).cpu().numpy())
+
+
+def test_iterative_mpc_driver_on_pendulum_env(cuda_device):
+    """learn_dynamics_iteratively_w_mpc (utils/iterative_mpc.py) end to end on the dependency-free pendulum env:
+    random-policy episodes -> train -> MPC episodes (shared handler, re-staged weights) -> retrain."""
+    from blackbox_mpc_b200.environment_utils import PendulumVecEnv
+    from blackbox_mpc_b200.policies.random_policy import RandomPolicy
+    from blackbox_mpc_b200.utils.iterative_mpc import learn_dynamics_iteratively_w_mpc
+    from blackbox_mpc_b200.utils.rollouts import perform_rollouts
+
+    class Writer:
+        def __init__(self):
+            self.rows = {}
+
+        def add_scalar(self, tag, value, step):
+            self.rows.setdefault(tag, []).append(value)
+
+    n = 4
+    env = PendulumVecEnv(num_of_agents=n, seed=0)
+    mlp = DeterministicMLP([4, 64, 64, 3], ["tanh", "tanh", None], seed=1)
+    writer = Writer()
+    handler, policy = learn_dynamics_iteratively_w_mpc(
+        env, number_of_initial_rollouts=8, number_of_rollouts_for_refinement=1, number_of_refinement_steps=1, task_horizon=60,
+        env_action_space=env.action_space, env_observation_space=env.observation_space,
+        initial_policy=RandomPolicy(n, env.action_space, seed=0), planning_horizon=12,
+        reward_function=pendulum.pendulum_reward_function, optimizer_name="CEM", num_agents=n, dynamics_function=mlp,
+        tf_writer=writer, epochs=20, learning_rate=2e-3, population_size=256, max_iterations=3, num_elite=16)
+    assert handler._training_iter == 2 and handler._model_training_in.shape[0] > 8 * 60 * n * 0.6
+    # the MPC episode was logged with the reference's tags; the learned model predicts the next observation well
+    err = writer.rows["states/predicted_observations_abs_error"]
+    assert len(err) == 60 and np.mean(err) < 0.25, np.mean(err)
+    assert "rewards/actual_episode_reward" in writer.rows and "system_model_val/loss" in writer.rows
+    obs, acts, rews = perform_rollouts(env, 1, 40, policy)
+    assert obs[0].shape == (41, n, 3) and acts[0].shape == (40, n, 1) and np.isfinite(rews[0]).all()
+    assert (acts[0] >= -2 - 1e-6).all() and (acts[0] <= 2 + 1e-6).all()
