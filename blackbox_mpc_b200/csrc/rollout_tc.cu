@@ -214,8 +214,8 @@ __device__ __forceinline__ void convert_full(uint32_t taddr, int c, const uint32
     for (int j = 0; j < 4; ++j)
       tanh_split_quad(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]),
                       hi[2 * j], lo[2 * j], hi[2 * j + 1], lo[2 * j + 1]);
-    tmem_st8(taddr + 16 * c, hi);
-    if (passes == 3) tmem_st8(taddr + 16 * c + 8, lo);
+    if (passes == 3) tmem_st16(taddr + 16 * c, hi, lo);
+    else tmem_st8(taddr + 16 * c, hi);
   } else {
     float v[16];
 #pragma unroll
