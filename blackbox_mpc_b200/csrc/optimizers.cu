@@ -529,8 +529,8 @@ void launch_penalty(const float* excess_sq, float* penalty, int64_t rows, int HU
 }
 void launch_topk_partial(const float* returns, const float* samples, float* partial, int P_local, int p0, int A, int HU, int E,
                          cudaStream_t st) {
-  static bool attr_set = false;   // opt in to > 48 KB of shared memory once (per process; the attribute is per function)
-  if (!attr_set) { cudaFuncSetAttribute(topk_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr_set = true; }
+  // opt in to > 48 KB of dynamic shared memory (per device and function: set on every launch, it is a host-side table write)
+  cudaFuncSetAttribute(topk_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int use_cache = (P_local > 0 && P_local <= 16384) ? 1 : 0;   // 64 KB of dynamic shared memory at most
   topk_partial_kernel<<<A, SEL_THREADS, use_cache ? P_local * sizeof(uint32_t) : 0, st>>>(returns, samples, partial, P_local, p0, A, HU, E, use_cache);
 }
