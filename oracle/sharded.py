@@ -66,3 +66,30 @@ def pi2_merge(partials, lamda):
     eta = (partials[:, :, 1] * scale).sum(dim=0)
     acc = (partials[:, :, 2:] * scale[:, :, None]).sum(dim=0)
     return acc / eta[:, None]
+
+
+def cmaes_partial(x_local, rewards_local, p0, num_elite):
+    """x_local [Pl, N] (clipped samples), rewards_local [Pl] (summed over agents, cma_es.py:158) ->
+    [E, 2+N] records (reward, global row, x), sorted (reward desc, row asc); unused slots hold -inf."""
+    Pl, N = x_local.shape
+    out = torch.zeros(num_elite, 2 + N, dtype=x_local.dtype)
+    out[:, 0] = -float("inf")
+    out[:, 1] = float(2 ** 31 - 1)
+    order = torch.sort(-rewards_local, stable=True).indices[:num_elite]
+    k = order.numel()
+    out[:k, 0] = rewards_local[order]
+    out[:k, 1] = (order + p0).to(out.dtype)
+    out[:k, 2:] = x_local[order]
+    return out
+
+
+def cmaes_merge(partials, num_elite):
+    """partials [G, E, 2+N] -> the E globally best rows in rank order (reward desc, global row asc): exactly the
+    first E rows of the reference's full argsort (cma_es.py:159), which are the only ones with non-zero
+    recombination weight (:62-68).  Returns (rows [E] int64, x_sorted [E, N])."""
+    G, E, rec = partials.shape
+    cand = partials.reshape(G * E, rec)
+    o1 = torch.sort(cand[:, 1], stable=True).indices
+    o2 = torch.sort(-cand[o1, 0], stable=True).indices
+    sel = o1[o2][:num_elite]
+    return cand[sel, 1].to(torch.int64), cand[sel, 2:]

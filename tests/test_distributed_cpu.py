@@ -99,3 +99,27 @@ def test_bench_reference_arm_rank0_only(tmp_path):
     line = json.loads(out0.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["n_gpus"] == 2
+
+
+def test_sharded_cmaes_selection_equals_unsharded():
+    """CMA-ES exchange (csrc/cmaes.cu: local top-E records -> exact global top-E): for any shard count the merged
+    elite rows, in rank order, are the first E rows of the unsharded descending argsort, ties to the lower row."""
+    import torch
+    from oracle import sharded
+    from blackbox_mpc_b200.sharding import shard_range, partial_floats
+    g = torch.Generator().manual_seed(3)
+    P, N, E = 203, 12, 16
+    x = torch.randn(P, N, generator=g, dtype=torch.float64)
+    rewards = torch.randn(P, generator=g, dtype=torch.float64)
+    rewards[17] = rewards[101] = rewards[5] = rewards.max() + 1.0        # a three-way tie at the top
+    ref_order = torch.sort(-rewards, stable=True).indices[:E]
+    assert ref_order[:3].tolist() == [5, 17, 101]
+    for world in (1, 2, 3, 8):
+        parts = []
+        for r in range(world):
+            p0, p1 = shard_range(P, r, world)
+            parts.append(sharded.cmaes_partial(x[p0:p1], rewards[p0:p1], p0, E))
+        assert parts[0].numel() == partial_floats("CMA-ES", 1, 2, 6, num_elite=E)   # N = A*H*dU = 12
+        rows, x_sorted = sharded.cmaes_merge(torch.stack(parts), E)
+        assert rows.tolist() == ref_order.tolist(), world
+        assert torch.equal(x_sorted, x[ref_order])
