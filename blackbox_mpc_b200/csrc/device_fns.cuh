@@ -9,7 +9,7 @@ namespace bbmpc {
 
 // ----------------------------------------------------------------------------- Philox4x32-10
 // Salmon et al., "Parallel random numbers: as easy as 1, 2, 3" (SC'11).  Checked against the
-// Random123 known-answer vectors in tests/test_sampler_host.py through bbmpc_philox4x32_host.
+// Random123 known-answer vectors in tests/test_cabi_cpu.py through bbmpc_philox4x32_host.
 struct Philox4 { uint32_t x, y, z, w; };
 
 __host__ __device__ inline uint32_t mulhi32(uint32_t a, uint32_t b) {

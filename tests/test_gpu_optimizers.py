@@ -176,3 +176,26 @@ def test_peer_memory_exchange_single_rank(cuda_device):
         torch.cuda.synchronize()
     ref_action2, _, _ = ref_policy._optimizer(torch.from_numpy(w.state), 1, False)
     assert torch.equal(action.cpu(), ref_action2.cpu())
+
+
+def test_sampler_distributions(cuda_device):
+    """The in-kernel Philox samplers follow the TF distributions they stand for [TF]: tf.random.truncated_normal
+    (cem.py:90-94: N(0,1) re-drawn until |z| <= 2, i.e. variance 1 - 4 phi(2) / (Phi(2) - Phi(-2)) = 0.7737) and
+    tf.random.uniform (random_search.py:40-41).  First-iteration draws of a fresh optimizer: mean = midpoint,
+    constrained variance = ((ub - lb) / 4)^2."""
+    w = workloads.make("C4", population_size=512, bias_scale=0.1)      # lb = -1, ub = +1: sigma = 0.5
+    _, _, samples, _, _, _ = _run_with_trace(w, "CEM")
+    x = samples[0].double().flatten()                                   # 512 * 30 * 6 = 92 160 draws
+    assert float(x.abs().max()) <= 1.0 + 1e-6                            # +-2 sigma support, no clipping needed
+    assert abs(float(x.mean())) < 0.006
+    assert abs(float(x.std()) - 0.5 * 0.7737 ** 0.5) < 0.004
+    z = x / 0.5
+    assert abs(float((z ** 4).mean()) / float((z ** 2).mean()) ** 2 - 2.3655) < 0.05   # kurtosis of N(0,1) truncated at 2 sigma
+    # independent across rows and time steps
+    s0 = samples[0][:, 0].double()
+    assert abs(float(torch.corrcoef(torch.stack([s0[:, 0, 0], s0[:, 1, 0]]))[0, 1])) < 0.15
+    assert abs(float(torch.corrcoef(torch.stack([s0[:-1, 0, 0], s0[1:, 0, 0]]))[0, 1])) < 0.15
+    _, _, samples_u, _, _, _ = _run_with_trace(w, "RandomSearch")
+    u = samples_u[0].double().flatten()
+    assert float(u.min()) >= -1.0 and float(u.max()) < 1.0
+    assert abs(float(u.mean())) < 0.008 and abs(float(u.var()) - 1.0 / 3.0) < 0.005
