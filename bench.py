@@ -13,8 +13,10 @@ of MEASURED_PEAKS.json.  `cpu_baseline` / `--impl reference` time the CPU restat
 reference's TF2 graph (oracle/, torch-CPU fp32, all host threads): TensorFlow 2.0 itself cannot be
 installed in this image, see DESIGN.md.
 
-For N>1 launch under torchrun (one rank per GPU): the population is sharded over the ranks, one
-NCCL all_gather of the refit partials per CEM iteration.
+For N>1 launch under torchrun (one rank per GPU): the population is sharded over the ranks; per CEM
+iteration the ranks exchange their elite records through peer memory (CUDA IPC buffers pulled over NVLink
+inside the merge-side kernel; BBMPC_P2P=0 or a failed IPC set-up falls back to one NCCL all_gather).
+`config.exchange` names the path used and `config.ranks_agree` whether all ranks computed the same action.
 """
 from __future__ import annotations
 
