@@ -116,6 +116,7 @@ struct bbmpc_ctx {
   // member-parallel rollout: per-group exchange of the members' raw outputs + arrival counters
   float* tc_xchg = nullptr; size_t tc_xchg_floats = 0;
   unsigned* tc_flags = nullptr; int tc_flags_n = 0;
+  float* pipe_park = nullptr; size_t pipe_park_floats = 0;   // pipelined rollout: parked member-tile states
   bool tc_no_groups = false;   // a cooperative launch did not fit: stay with one CTA per tile
   void* dbg_host = nullptr;  // BBMPC_DEBUG=1: host-mapped watchdog record of the tensor-core kernel
   // rollout-kernel timing (bbmpc_profile_*): event pairs recorded around every rollout launch
@@ -155,6 +156,9 @@ int launch_rollout_simt(bbmpc_ctx* ctx, const float* states, const float* action
 int launch_step_simt(bbmpc_ctx* ctx, const StepIO& io, cudaStream_t st);
 int launch_rollout_tc(bbmpc_ctx* ctx, const float* states, const float* actions, float* returns,
                       const float* penalty, int rows, int A, int H, int passes, cudaStream_t st);
+// pipelined two-jobs-in-flight variant (rollout_pipe.cu); returns -100 when the model does not fit it
+int launch_rollout_pipe(bbmpc_ctx* ctx, const float* states, const float* actions, float* returns,
+                        const float* penalty, int rows, int A, int H, int passes, cudaStream_t st);
 int pack_tc_image(bbmpc_ctx* ctx, cudaStream_t st);   // builds model.wimg from model.w32
 bool tc_supported(const ModelHost& m, std::string* why);
 uint32_t tc_idesc(int Npad);  // instruction descriptor of the rollout kernel's MMAs

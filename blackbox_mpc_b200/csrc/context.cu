@@ -135,9 +135,15 @@ int rollout_dispatch(bbmpc_ctx* ctx, const float* states, const float* actions, 
   int rc;
   if (prec == BBMPC_PREC_FP32)
     rc = launch_rollout_simt(ctx, states, actions, returns, penalty, rows, A, H, 0, st);
-  else
-    rc = launch_rollout_tc(ctx, states, actions, returns, penalty, rows, A, H,
-                           prec == BBMPC_PREC_BF16 ? 1 : 3, st);
+  else {
+    // pipelined kernel (two jobs in flight per CTA) when the model fits its TMEM / shared-memory budget;
+    // BBMPC_TC_PIPE=0 keeps the one-tile-per-CTA kernel (A/B measurements)
+    const int passes = prec == BBMPC_PREC_BF16 ? 1 : 3;
+    const char* pipe_env = getenv("BBMPC_TC_PIPE");
+    rc = -100;
+    if (H > 0 && !(pipe_env && pipe_env[0] == '0')) rc = launch_rollout_pipe(ctx, states, actions, returns, penalty, rows, A, H, passes, st);
+    if (rc == -100) rc = launch_rollout_tc(ctx, states, actions, returns, penalty, rows, A, H, passes, st);
+  }
   if (rc == BBMPC_OK && e1) {
     BB_CUDA(ctx, cudaEventRecord(e1, st));
     ctx->prof_n++;
@@ -186,7 +192,7 @@ void bbmpc_ctx_destroy(bbmpc_ctx* ctx) {
   free_model(ctx->model);
   cudaFree(ctx->model.norm_buf);
   cudaFree(ctx->step_scratch); cudaFree(ctx->step_counters);
-  cudaFree(ctx->tc_xchg); cudaFree(ctx->tc_flags);
+  cudaFree(ctx->tc_xchg); cudaFree(ctx->tc_flags); cudaFree(ctx->pipe_park);
   if (ctx->dbg_host) cudaFreeHost(ctx->dbg_host);
   for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
   delete ctx;
