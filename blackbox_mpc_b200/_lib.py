@@ -19,6 +19,7 @@ OPT_CEM, OPT_PI2, OPT_RANDOM_SEARCH, OPT_PSO, OPT_SPSA, OPT_CMAES = 1, 2, 3, 4, 
 PRECISIONS = {"auto": PREC_AUTO, "fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 
 c_float_p = C.POINTER(C.c_float)
+MIN_VERSION = 200
 
 
 class OptConfig(C.Structure):
@@ -37,6 +38,7 @@ class OptConfig(C.Structure):
 _VP, _I, _I64, _U64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
 SIGNATURES = {
     "bbmpc_version": (_I, []),
+    "bbmpc_abi_config_size": (_I, []),
     "bbmpc_last_error": (C.c_char_p, [_VP]),
     "bbmpc_ctx_create": (_I, [_I, _U64, C.POINTER(_VP)]),
     "bbmpc_ctx_destroy": (None, [_VP]),
@@ -84,7 +86,9 @@ class BBMPCError(RuntimeError):
 
 
 def load() -> C.CDLL:
-    """Loads (building first if the in-tree .so is missing or stale and nvcc exists)."""
+    """Loads the in-tree library, building it first when it is missing (nvcc cross-compiles without a GPU).  A library
+    that does not match this binding (older version, different bbmpc_opt_config layout, missing symbol) is rejected
+    here instead of corrupting configurations later: rebuild with `python -m blackbox_mpc_b200._build`."""
     global _lib
     if _lib is not None:
         return _lib
@@ -95,6 +99,10 @@ def load() -> C.CDLL:
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header/library drift: fail loudly
         fn.restype, fn.argtypes = res, args
+    if lib.bbmpc_version() < MIN_VERSION or lib.bbmpc_abi_config_size() != C.sizeof(OptConfig):
+        raise ImportError(f"{LIB_PATH} is stale (version {lib.bbmpc_version()}, bbmpc_opt_config of "
+                          f"{lib.bbmpc_abi_config_size()} bytes; this binding needs >= {MIN_VERSION} and "
+                          f"{C.sizeof(OptConfig)} bytes): run `python -m blackbox_mpc_b200._build --force`")
     _lib = lib
     return lib
 

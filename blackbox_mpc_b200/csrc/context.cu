@@ -157,7 +157,8 @@ using namespace bbmpc;
 
 extern "C" {
 
-int bbmpc_version(void) { return 100; }
+int bbmpc_version(void) { return 200; }
+int bbmpc_abi_config_size(void) { return static_cast<int>(sizeof(bbmpc_opt_config)); }
 
 const char* bbmpc_last_error(const bbmpc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 

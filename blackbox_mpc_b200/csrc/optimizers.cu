@@ -492,8 +492,11 @@ __global__ void p2p_publish_kernel(uint32_t* flag, uint32_t seq) {
   __threadfence_system();
   asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag), "r"(seq) : "memory");
 }
-__global__ void __launch_bounds__(256) p2p_gather_kernel(float* const* peers, float* gathered, int n_floats, size_t flag_off_floats,
-                                                         uint32_t seq, int parity) {
+// `src_stride` (a multiple of 4 floats) separates the two parity copies of a message inside a rank's exchange buffer, so
+// the 16-byte loads are aligned for any message length; the gathered copies stay dense (n_floats apart), hence the
+// vector path only when n_floats itself is a multiple of 4.
+__global__ void __launch_bounds__(256) p2p_gather_kernel(float* const* peers, float* gathered, int n_floats, int src_stride,
+                                                         size_t flag_off_floats, uint32_t seq, int parity) {
   const int g = blockIdx.x;
   const float* src_base = peers[g];
   if (threadIdx.x == 0) {
@@ -505,16 +508,18 @@ __global__ void __launch_bounds__(256) p2p_gather_kernel(float* const* peers, fl
     } while (seen < seq);
   }
   __syncthreads();
-  const float4* src = reinterpret_cast<const float4*>(src_base + static_cast<size_t>(parity) * n_floats);
+  const float* msg = src_base + static_cast<size_t>(parity) * src_stride;
+  const int n_vec = (n_floats & 3) == 0 ? n_floats / 4 : 0;
+  const float4* src = reinterpret_cast<const float4*>(msg);
   float4* dst = reinterpret_cast<float4*>(gathered + static_cast<size_t>(g) * n_floats);
-  for (int i = threadIdx.x; i < n_floats / 4; i += blockDim.x) {
+  for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
     float4 v;
     asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + i) : "memory");
     dst[i] = v;
   }
-  for (int i = (n_floats / 4) * 4 + threadIdx.x; i < n_floats; i += blockDim.x) {
+  for (int i = 4 * n_vec + threadIdx.x; i < n_floats; i += blockDim.x) {
     float v;
-    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(src_base + static_cast<size_t>(parity) * n_floats + i) : "memory");
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(msg + i) : "memory");
     gathered[static_cast<size_t>(g) * n_floats + i] = v;
   }
 }
@@ -891,10 +896,11 @@ int bbmpc_opt_call(bbmpc_opt* o, const float* state, int time_step, int add_nois
       const int nf = partial_floats(o);
       const uint32_t seq = ++o->p2p_seq;
       const int parity = static_cast<int>(seq & 1u);
-      if (int rc = bbmpc_opt_iter_local(o, it, o->p2p_buf + static_cast<size_t>(parity) * nf, stream)) return rc;
-      const size_t flag_off = 2 * static_cast<size_t>(nf);
+      const int stride4 = (nf + 3) & ~3;     // parity copies 16-byte aligned for any message length
+      if (int rc = bbmpc_opt_iter_local(o, it, o->p2p_buf + static_cast<size_t>(parity) * stride4, stream)) return rc;
+      const size_t flag_off = 2 * static_cast<size_t>(stride4);
       p2p_publish_kernel<<<1, 1, 0, st>>>(reinterpret_cast<uint32_t*>(o->p2p_buf + flag_off), seq); BB_LAUNCH_CHECK(o->ctx);
-      p2p_gather_kernel<<<o->world, 256, 0, st>>>(o->d_peer, o->d_gather, nf, flag_off, seq, parity); BB_LAUNCH_CHECK(o->ctx);
+      p2p_gather_kernel<<<o->world, 256, 0, st>>>(o->d_peer, o->d_gather, nf, stride4, flag_off, seq, parity); BB_LAUNCH_CHECK(o->ctx);
       if (int rc = bbmpc_opt_iter_merge(o, it, o->d_gather, o->world, stream)) return rc;
       continue;
     }
@@ -931,7 +937,7 @@ int bbmpc_opt_p2p_export(bbmpc_opt* o, void* handle_out_host, void** ptr_out_hos
   bbmpc_ctx* ctx = o->ctx;
   BB_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!o->p2p_buf) {
-    const size_t nf = static_cast<size_t>(partial_floats(o));
+    const size_t nf = (static_cast<size_t>(partial_floats(o)) + 3) & ~static_cast<size_t>(3);
     o->p2p_bytes = (2 * nf + 16) * sizeof(float);
     BB_CUDA(ctx, cudaMalloc(&o->p2p_buf, o->p2p_bytes));     // own allocation: an IPC handle exports the whole allocation
     o->owned.push_back(o->p2p_buf);

@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
       float s[DS_T];
       float ret = 0.0f;
       // initial state and the layer-0 operand of step 0
-      for (int i = n_mt - 1; i >= 0; --i) {
+      for (int i = 0; i < n_mt; ++i) {
         const int row = mt_tile(r, i) * PIPE_ROWS + row_in_tile;
         const int arow = row < p.rows ? row : 0;
         const float* srow_ptr = p.states + static_cast<size_t>(arow % p.A) * p.dS;

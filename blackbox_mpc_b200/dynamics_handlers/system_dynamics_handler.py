@@ -81,9 +81,17 @@ class SystemDynamicsHandler:
             if self._is_normalized:   # same six file names as the reference (:84-95)
                 self.set_normalization(*[np.load(os.path.join(saved_model_dir, n + ".npy")) for n in _STAT_NAMES])
             saved = training.load_weights(saved_model_dir)
-            if saved is not None and dynamics_function is not None and hasattr(dynamics_function, "members"):
+            if saved is not None:
+                if dynamics_function is None or not hasattr(dynamics_function, "members"):
+                    # the reference restores the whole model from the directory (:78-83); weights.npz carries no
+                    # activation list, so a model object of the right shape must be supplied instead of dropping them
+                    raise ValueError("saved_model_dir holds trained weights: pass the DeterministicMLP / EnsembleMLP "
+                                     "they belong to as dynamics_function")
                 for member, (ws, bs) in zip(dynamics_function.members(), saved):
                     member.set_weights(ws, bs)
+            # the loaded statistics are the ones the loaded weights were trained against: keep them when train() is
+            # called later (reference :80-83 sets _first_time = False after loading)
+            self._first_time = False
 
     # -- statistics ---------------------------------------------------------------------------
     def set_normalization(self, mean_states, std_states, mean_actions, std_actions, mean_targets, std_targets):

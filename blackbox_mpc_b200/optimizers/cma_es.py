@@ -12,7 +12,7 @@ class CMAESOptimizer(OptimizerBase):
     KIND = _lib.OPT_CMAES
 
     def __init__(self, env_action_space, env_observation_space, planning_horizon=50, max_iterations=5,
-                 population_size=500, num_elite=50, h_sigma=1.0, alpha_cov=2.0, num_agents=5):
+                 population_size=500, num_elite=50, num_agents=5, alpha_cov=2.0, h_sigma=1.0):   # reference order (cma_es.py:7-9)
         super().__init__(name=None, planning_horizon=planning_horizon, max_iterations=max_iterations,
                          num_agents=num_agents, env_action_space=env_action_space,
                          env_observation_space=env_observation_space)

@@ -64,6 +64,9 @@ typedef struct bbmpc_opt bbmpc_opt;
 
 /* ---- library / context ------------------------------------------------------------------ */
 int bbmpc_version(void);
+/* sizeof(bbmpc_opt_config) as the library was compiled: bindings compare it with their own mirror of the struct
+ * so that a stale libbbmpc.so fails loudly instead of reading a config with shifted fields. */
+int bbmpc_abi_config_size(void);
 /* Text of the last error on this ctx (or of the last failed bbmpc_ctx_create when ctx == NULL). */
 const char* bbmpc_last_error(const bbmpc_ctx* ctx);
 /* One context per process per GPU.  `seed` keys every Philox stream drawn by this context. */

@@ -154,12 +154,19 @@ def test_shard_invariance_single_gpu(cuda_device):
             assert torch.equal(act.cpu(), ref_action.cpu())
 
 
-def test_peer_memory_exchange_single_rank(cuda_device):
+@pytest.mark.parametrize("opt_name,opt_args,H,A", [
+    ("CEM", dict(num_elite=16, alpha=0.25), 30, 2),       # 2 * 16 * 32 floats: 16-byte vector path
+    ("CEM", dict(num_elite=5, alpha=0.25), 15, 1),        # 5 * 17 = 85 floats: not a multiple of 4
+    ("PI2", dict(lamda=1.0), 15, 3),                      # 3 * 17 = 51 floats
+    ("RandomSearch", dict(), 13, 1),                      # 15 floats
+])
+def test_peer_memory_exchange_single_rank(cuda_device, opt_name, opt_args, H, A):
     """bbmpc_opt_p2p_export / _connect with world = 1 (the rank pulls its own message through the exchange
-    buffer): publish -> flag wait -> gather -> merge must reproduce the plain path bit for bit."""
+    buffer): publish -> flag wait -> gather -> merge must reproduce the plain path bit for bit, for message
+    lengths that are and are not multiples of 4 floats (the parity copies are 16-byte aligned either way)."""
     import ctypes as C
-    w = workloads.make("C2", population_size=300, num_agents=2, bias_scale=0.1)
-    w.optimizer_args = dict(num_elite=16, alpha=0.25)
+    w = workloads.make("C2", population_size=300, num_agents=A, planning_horizon=H, bias_scale=0.1)
+    w.optimizer_name, w.optimizer_args = opt_name, dict(opt_args)
     ref_policy = workloads.build_policy(w, precision="fp32")
     ref_action, ref_next, _ = ref_policy._optimizer(torch.from_numpy(w.state), 0, False)
     policy = workloads.build_policy(w, precision="fp32")
@@ -171,11 +178,11 @@ def test_peer_memory_exchange_single_rank(cuda_device):
     assert ptr.value
     ptrs = (C.c_void_p * 1)(ptr.value)
     e.check(e.lib.bbmpc_opt_p2p_connect(opt._handle, None, ptrs))
-    for t in range(2):      # twice: sequence numbers / buffer parity advance across act() calls
+    for t in range(3):      # sequence numbers / buffer parity advance across act() calls (odd and even parity)
         action, nxt, _ = opt(torch.from_numpy(w.state), t, False)
         torch.cuda.synchronize()
-    ref_action2, _, _ = ref_policy._optimizer(torch.from_numpy(w.state), 1, False)
-    assert torch.equal(action.cpu(), ref_action2.cpu())
+        ref_action_t, _, _ = ref_policy._optimizer(torch.from_numpy(w.state), t, False) if t else (ref_action, None, None)
+        assert torch.equal(action.cpu(), ref_action_t.cpu()), f"act() call {t}"
 
 
 def test_sampler_distributions(cuda_device):

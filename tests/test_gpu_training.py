@@ -72,6 +72,13 @@ def test_train_then_act_and_reload(cuda_device, tmp_path):
     ev2 = DeterministicTrajectoryEvaluator(reward_function=pendulum.pendulum_reward_function, system_dynamics_handler=handler2)
     st, ac = torch.from_numpy(s0[None]), torch.from_numpy(action[None])
     np.testing.assert_array_equal(ev1.predict_next_state(st, ac).cpu().numpy(), ev2.predict_next_state(st, ac).cpu().numpy())
+    # the loaded statistics survive a later train() (reference :80-83: _first_time = False after loading) ...
+    stats_loaded = [t.clone() for t in handler2._stats]
+    handler2.train(*_episodes(2, 50, 4, rng), None, epochs=1)
+    assert all(torch.equal(a, b) for a, b in zip(stats_loaded, handler2._stats))
+    # ... and a directory with trained weights is never silently dropped
+    with pytest.raises(ValueError):
+        SystemDynamicsHandler(act_space, obs_space, dynamics_function=None, is_normalized=True, saved_model_dir=d, seed=0)
 
 
 def test_iterative_mpc_driver_on_pendulum_env(cuda_device):
