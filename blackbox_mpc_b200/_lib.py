@@ -71,6 +71,7 @@ SIGNATURES = {
     "bbmpc_opt_p2p_connect": (_I, [_VP, _VP, C.POINTER(_VP)]),
     "bbmpc_opt_get_tensor": (_I64, [_VP, C.c_char_p, _VP, _I64, _VP]),
     "bbmpc_opt_set_sample_trace": (_I, [_VP, _VP, _I64]),
+    "bbmpc_opt_set_draw_injection": (_I, [_VP, _VP, _I64]),
     "bbmpc_philox4x32_host": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
 }
 

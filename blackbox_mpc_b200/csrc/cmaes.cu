@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) cmaes_sample_kernel(const float* __restri
                                                            const float* __restrict__ sigma, const float* __restrict__ lb,
                                                            const float* __restrict__ ub, float* __restrict__ x,
                                                            float* __restrict__ excess_sq, float* __restrict__ z_trace,
-                                                           int P_local, int p0, int N, int dU, uint64_t seed,
+                                                           const float* __restrict__ z_inject, int P_local, int p0, int N, int dU, uint64_t seed,
                                                            uint32_t act_call, uint32_t iter) {
   __shared__ float zs[CK][CT + 1];
   __shared__ float bs[CK][CT];
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) cmaes_sample_kernel(const float* __restri
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int k = k0 + kq + j;
-        const float zv = (row < P_local && k < N) ? std_normal(ws[j]) : 0.0f;
+        const float zv = (row < P_local && k < N) ? (z_inject ? z_inject[static_cast<size_t>(p0 + row) * N + k] : std_normal(ws[j])) : 0.0f;
         zs[kq + j][r] = zv;
         if (z_trace && blockIdx.y == 0 && row < P_local && k < N) z_trace[static_cast<size_t>(row) * N + k] = zv;
       }
@@ -340,8 +340,15 @@ int cmaes_iter_local(bbmpc_opt* o, int iter, float* partial, cudaStream_t st) {
     const int64_t per_iter = static_cast<int64_t>(o->P_local) * N;
     float* z_trace = (o->trace && (static_cast<int64_t>(iter) + 1) * per_iter <= o->trace_floats) ? o->trace + iter * per_iter : nullptr;
     dim3 grid(grid_for(o->P_local, CT), grid_for(N, CT));
+    const float* z_inject = nullptr;
+    if (o->inject) {   // one block of [P, N] standard normals per iteration since bbmpc_opt_set_draw_injection
+      const int64_t blk = static_cast<int64_t>(c.population_size) * N;
+      if ((o->inject_iter + 1) * blk > o->inject_floats) return fail(ctx, BBMPC_EINVAL, "draw injection buffer exhausted");
+      z_inject = o->inject + o->inject_iter * blk;
+      ++o->inject_iter;
+    }
     cmaes_sample_kernel<<<grid, 256, 0, st>>>(o->d_BD, o->d_m, o->d_sigma, o->d_lb, o->d_ub, o->d_samples, o->d_work, z_trace,
-                                              o->P_local, o->p0, N, c.dU, ctx->seed, o->act_call, static_cast<uint32_t>(iter));
+                                              z_inject, o->P_local, o->p0, N, c.dU, ctx->seed, o->act_call, static_cast<uint32_t>(iter));
     BB_LAUNCH_CHECK(ctx);
     const int64_t rows = static_cast<int64_t>(o->P_local) * A;
     launch_penalty(o->d_work, o->d_penalty, rows, o->HU, st); BB_LAUNCH_CHECK(ctx);

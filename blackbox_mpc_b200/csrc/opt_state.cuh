@@ -29,7 +29,7 @@ struct bbmpc_opt {
   float* d_next = nullptr;        // [A,dS]
   float* d_reward = nullptr;      // [A]
   // PSO
-  float *d_v = nullptr, *d_pbx = nullptr, *d_pbr = nullptr, *d_gbx = nullptr, *d_gbr = nullptr, *d_sol = nullptr;
+  float *d_v = nullptr, *d_pbx = nullptr, *d_pbr = nullptr, *d_gbx = nullptr, *d_gbr = nullptr, *d_sol = nullptr, *d_pso_r = nullptr;
   // CMA-ES
   float *d_m = nullptr, *d_sigma = nullptr, *d_C = nullptr, *d_B = nullptr, *d_D = nullptr, *d_ps = nullptr,
         *d_pc = nullptr, *d_z = nullptr, *d_BD = nullptr, *d_work = nullptr, *d_cma_w = nullptr;
@@ -43,6 +43,8 @@ struct bbmpc_opt {
   uint32_t p2p_seq = 0;            // exchanges published so far (monotonic over the handle's lifetime)
   // trace + pinned staging
   float* trace = nullptr; int64_t trace_floats = 0;
+  // injected standard variates (tests: committed golden draws): block k serves the k-th iteration since it was set
+  const float* inject = nullptr; int64_t inject_floats = 0; int64_t inject_iter = 0;
   float* h_pinned = nullptr;
   std::vector<void*> owned;
 };

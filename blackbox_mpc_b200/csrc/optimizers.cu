@@ -77,6 +77,7 @@ struct SampleArgs {
   int P_local, p0, A, H, dU; uint64_t seed; uint32_t act_call, iter;
   float ck;   // SPSA perturbation size
   float* raw_trace;  // optional: un-clipped draws of this iteration (PI2), for oracle injection
+  const float* inject;  // optional: this iteration's standard variates [P, A, H*dU] by GLOBAL row, instead of Philox
 };
 
 // cem.py:81-94: cvar = min(((mean-lb)/2)^2, ((ub-mean)/2)^2, var); x = mean + sqrt(cvar)*tn
@@ -95,7 +96,8 @@ __global__ void cem_sample_kernel(const SampleArgs s) {
     const float m = s.mean[a * HU + e];
     const float lo = __fdiv_rn(__fsub_rn(m, s.lb[u]), 2.0f), hi = __fdiv_rn(__fsub_rn(s.ub[u], m), 2.0f);
     const float cvar = fminf(fminf(__fmul_rn(lo, lo), __fmul_rn(hi, hi)), s.var[a * HU + e]);
-    s.samples[pa * HU + e] = __fadd_rn(__fmul_rn(std_truncnorm(w[j]), sqrtf(cvar)), m);
+    const float z = s.inject ? s.inject[(static_cast<int64_t>(s.p0 + p) * s.A + a) * HU + e] : std_truncnorm(w[j]);
+    s.samples[pa * HU + e] = __fadd_rn(__fmul_rn(z, sqrtf(cvar)), m);
   }
 }
 // pi2.py:65-76: x = mean + sqrt(var)*tn; clip; penalty[p,a] = ||x - clip(x)||^2 (summed by a
@@ -113,7 +115,8 @@ __global__ void pi2_sample_kernel(const SampleArgs s, float* raw_excess_sq) {
     const int e = 4 * blk + j;
     if (e >= HU) break;
     const int u = e % s.dU;
-    const float x = __fadd_rn(__fmul_rn(std_truncnorm(w[j]), sqrtf(s.var[a * HU + e])), s.mean[a * HU + e]);
+    const float z = s.inject ? s.inject[(static_cast<int64_t>(s.p0 + p) * s.A + a) * HU + e] : std_truncnorm(w[j]);
+    const float x = __fadd_rn(__fmul_rn(z, sqrtf(s.var[a * HU + e])), s.mean[a * HU + e]);
     const float xf = fminf(fmaxf(x, s.lb[u]), s.ub[u]);
     const float d = __fsub_rn(x, xf);
     s.samples[pa * HU + e] = xf;
@@ -134,7 +137,8 @@ __global__ void rs_sample_kernel(const SampleArgs s) {
     const int e = 4 * blk + j;
     if (e >= HU) break;
     const int u = e % s.dU;
-    s.samples[pa * HU + e] = __fadd_rn(__fmul_rn(u01_halfopen(w[j]), __fsub_rn(s.ub[u], s.lb[u])), s.lb[u]);
+    const float u01 = s.inject ? s.inject[(static_cast<int64_t>(s.p0 + p) * s.A + a) * HU + e] : u01_halfopen(w[j]);
+    s.samples[pa * HU + e] = __fadd_rn(__fmul_rn(u01, __fsub_rn(s.ub[u], s.lb[u])), s.lb[u]);
   }
 }
 // spsa.py:73-91: delta = +-1; theta+- = sol +- ck*delta; clip; excess^2 (plus rows first, then minus)
@@ -151,7 +155,7 @@ __global__ void spsa_sample_kernel(const SampleArgs s, float* raw_excess_sq) {
     const int e = 4 * blk + j;
     if (e >= HU) break;
     const int u = e % s.dU;
-    const float delta = (w[j] >> 31) ? 1.0f : -1.0f;
+    const float delta = s.inject ? s.inject[(static_cast<int64_t>(s.p0 + p) * s.A + a) * HU + e] : ((w[j] >> 31) ? 1.0f : -1.0f);
     const float step = __fmul_rn(s.ck, delta), m = s.mean[a * HU + e];
     const float xp = __fadd_rn(m, step), xm = __fsub_rn(m, step);
     const float xpf = fminf(fmaxf(xp, s.lb[u]), s.ub[u]), xmf = fminf(fmaxf(xm, s.lb[u]), s.ub[u]);
@@ -392,7 +396,7 @@ __global__ void argmax_merge_kernel(const float* partials, int world, int HU, fl
 
 // ---- SPSA partial: sum_p (r+ - r-) / (2 ck delta) per (a,e) (spsa.py:98-103); delta regenerated
 __global__ void spsa_partial_kernel(const float* returns, float* partial, int P_local, int p0, int A, int HU,
-                                    float ck, uint64_t seed, uint32_t act_call, uint32_t iter) {
+                                    float ck, uint64_t seed, uint32_t act_call, uint32_t iter, const float* inject) {
   // one warp per (a, e): lanes stride the population, fixed-order tree reduction
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= A * HU) return;
@@ -402,7 +406,7 @@ __global__ void spsa_partial_kernel(const float* returns, float* partial, int P_
   for (int p = lane; p < P_local; p += 32) {
     const Philox4 r = draw_block(seed, act_call, STREAM_SAMPLES, iter, (p0 + p) * A + a, e >> 2);
     const uint32_t word = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
-    const float delta = (word >> 31) ? 1.0f : -1.0f;
+    const float delta = inject ? inject[(static_cast<int64_t>(p0 + p) * A + a) * HU + e] : ((word >> 31) ? 1.0f : -1.0f);
     const float diff = __fsub_rn(returns[p * A + a], returns[half + p * A + a]);
     acc += __fdiv_rn(diff, __fmul_rn(__fmul_rn(2.0f, ck), delta));
   }
@@ -443,11 +447,12 @@ __global__ void pso_pbest_r_kernel(const float* rewards, float* pbr, int64_t row
 }
 // velocity / position update (pso.py:107-111); r1, r2: ONE N(0,1) scalar each per iteration
 __global__ void pso_move_kernel(float* x, float* v, const float* pbx, const float* gbx, int64_t n, int AHU, float w,
-                                float c1, float c2, uint64_t seed, uint32_t act_call, uint32_t iter) {
+                                float c1, float c2, uint64_t seed, uint32_t act_call, uint32_t iter, float* r_record) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Philox4 r = draw_block(seed, act_call, STREAM_PSO_R, iter, 0, 0);
   const float r1 = std_normal(r.x), r2 = std_normal(r.y);
+  if (i == 0 && r_record) { r_record[2 * iter] = r1; r_record[2 * iter + 1] = r2; }   // inspection: get_tensor("pso_r")
   const float xi = x[i];
   const float nv = __fadd_rn(__fadd_rn(__fmul_rn(v[i], w), __fmul_rn(__fmul_rn(__fsub_rn(pbx[i], xi), c1), r1)),
                              __fmul_rn(__fmul_rn(__fsub_rn(gbx[i % AHU], xi), c2), r2));
@@ -582,7 +587,7 @@ int bbmpc_opt_create(bbmpc_ctx* ctx, const bbmpc_opt_config* cfg, bbmpc_opt** ou
   A_(dalloc(o, &o->d_state, A * dS)); A_(dalloc(o, &o->d_mean, o->AHU)); A_(dalloc(o, &o->d_var, o->AHU));
   A_(dalloc(o, &o->d_prev, o->AHU)); A_(dalloc(o, &o->d_var0, o->AHU));
   A_(dalloc(o, &o->d_action, A * dU)); A_(dalloc(o, &o->d_next, A * dS)); A_(dalloc(o, &o->d_reward, A));
-  if (cfg->kind == BBMPC_OPT_PSO) { A_(dalloc(o, &o->d_gbx, o->AHU)); A_(dalloc(o, &o->d_gbr, A)); A_(dalloc(o, &o->d_sol, A * dU)); }
+  if (cfg->kind == BBMPC_OPT_PSO) { A_(dalloc(o, &o->d_gbx, o->AHU)); A_(dalloc(o, &o->d_gbr, A)); A_(dalloc(o, &o->d_sol, A * dU)); A_(dalloc(o, &o->d_pso_r, 128)); }
   if (rc == BBMPC_OK && cudaMallocHost(reinterpret_cast<void**>(&o->h_pinned), (A * dS * 2 + A * dU + A) * sizeof(float)) != cudaSuccess)
     rc = fail(ctx, BBMPC_ENOMEM, "cudaMallocHost failed");
   if (rc != BBMPC_OK) { bbmpc_opt_destroy(o); return rc; }
@@ -728,7 +733,15 @@ int bbmpc_opt_iter_local(bbmpc_opt* o, int iter, float* partial_out, void* strea
   float* partial = partial_out ? partial_out : o->d_partial;
   if (c.kind == BBMPC_OPT_CMAES) return cmaes_iter_local(o, iter, partial, st);
   SampleArgs s{o->d_samples, o->d_penalty, o->d_mean, o->d_var, o->d_lb, o->d_ub, o->P_local, o->p0, A, H, dU,
-               ctx->seed, o->act_call, static_cast<uint32_t>(iter), 0.0f, nullptr};
+               ctx->seed, o->act_call, static_cast<uint32_t>(iter), 0.0f, nullptr, nullptr};
+  {  // injected standard variates: one block of [P, A, H*dU] per iteration since bbmpc_opt_set_draw_injection
+    const int64_t blk = static_cast<int64_t>(c.population_size) * A * HU;
+    if (o->inject && c.kind != BBMPC_OPT_PSO) {
+      if ((o->inject_iter + 1) * blk > o->inject_floats) return opt_fail(o, BBMPC_EINVAL, "draw injection buffer exhausted");
+      s.inject = o->inject + o->inject_iter * blk;
+      ++o->inject_iter;
+    }
+  }
   const int64_t rows = static_cast<int64_t>(o->n_eval) * A;
   const int64_t nthr = static_cast<int64_t>(o->P_local) * A * ((HU + 3) / 4);
   const float* penalty = nullptr;
@@ -781,7 +794,7 @@ int bbmpc_opt_iter_local(bbmpc_opt* o, int iter, float* partial_out, void* strea
     case BBMPC_OPT_SPSA:
       spsa_partial_kernel<<<grid_for(static_cast<int64_t>(A) * HU * 32, 256), 256, 0, st>>>(
           o->d_returns, partial, o->P_local, o->p0, A, HU, c.noise_parameter / powf(static_cast<float>(iter) + 1.0f, c.gamma),
-          ctx->seed, o->act_call, static_cast<uint32_t>(iter));
+          ctx->seed, o->act_call, static_cast<uint32_t>(iter), s.inject);
       break;
     case BBMPC_OPT_PSO: {
       pso_pbest_kernel<<<grid_for(rows * HU, 256), 256, 0, st>>>(o->d_samples, o->d_returns, o->d_pbx, o->d_pbr, rows, HU); BB_LAUNCH_CHECK(ctx);
@@ -829,7 +842,8 @@ int bbmpc_opt_iter_merge(bbmpc_opt* o, int iter, const float* partials, int worl
       const int64_t n = static_cast<int64_t>(o->P_local) * o->AHU;
       if (n > 0)
         pso_move_kernel<<<grid_for(n, 256), 256, 0, st>>>(o->d_samples, o->d_v, o->d_pbx, o->d_gbx, n, o->AHU, c.w, c.c1, c.c2,
-                                                          ctx->seed, o->act_call, static_cast<uint32_t>(iter));
+                                                          ctx->seed, o->act_call, static_cast<uint32_t>(iter),
+                                                          iter < 64 ? o->d_pso_r : nullptr);
       else return BBMPC_OK;
       break;
     }
@@ -999,6 +1013,7 @@ int64_t bbmpc_opt_get_tensor(bbmpc_opt* o, const char* name, float* out, int64_t
   else if (s == "pbest_r") { src = o->d_pbr; n = pop; }
   else if (s == "gbest_x") { src = o->d_gbx; n = o->AHU; }
   else if (s == "gbest_r") { src = o->d_gbr; n = A; }
+  else if (s == "pso_r") { src = o->d_pso_r; n = o->d_pso_r ? 128 : 0; }   // (r1, r2) of the iterations of the last act() call
   if (o->cfg.kind == BBMPC_OPT_CMAES) {   // tf.Variables of cma_es.py:95-117 (D as its diagonal)
     const int64_t N = o->AHU;
     if (s == "m") { src = o->d_mean; n = N; }
@@ -1016,6 +1031,13 @@ int64_t bbmpc_opt_get_tensor(bbmpc_opt* o, const char* name, float* out, int64_t
     if (e != cudaSuccess) return fail(ctx, BBMPC_ECUDA, "get_tensor copy: %s", cudaGetErrorString(e));
   }
   return n;
+}
+
+int bbmpc_opt_set_draw_injection(bbmpc_opt* o, const float* std_draws, int64_t n_floats) {
+  if (!o) return BBMPC_EINVAL;
+  if (o->cfg.kind == BBMPC_OPT_PSO) return opt_fail(o, BBMPC_EINVAL, "draw injection is not available for PSO");
+  o->inject = std_draws; o->inject_floats = std_draws ? n_floats : 0; o->inject_iter = 0;
+  return BBMPC_OK;
 }
 
 int bbmpc_opt_set_sample_trace(bbmpc_opt* o, float* trace, int64_t n_floats) {

@@ -51,8 +51,9 @@ constexpr int PIPE_MAX_MT = 3;          // member-tiles per CTA and round
 constexpr int PIPE_MAX_WSTAGES = 8;
 constexpr int PIPE_MAX_UNITS = 16;      // A-ring positions
 constexpr int PIPE_ROWS = 128;
-// register budgets per warpgroup role (setmaxnreg; 640 threads start at 96): 128 * (64 + 40 + 152 + 2 * 128) = 65536
-constexpr int PIPE_REGS_CTRL = 64, PIPE_REGS_PUB = 40, PIPE_REGS_INT = 152, PIPE_REGS_CONV = 128;
+// register budgets per warpgroup role.  setmaxnreg moves registers inside the CTA's LAUNCH allocation (640 threads x 96), not the
+// SM's file: the budgets must sum to 5 warpgroups x 96 = 480 (64 + 32 + 144 + 2 x 120), or the last setmaxnreg.inc never returns.
+constexpr int PIPE_REGS_CTRL = 64, PIPE_REGS_PUB = 32, PIPE_REGS_INT = 144, PIPE_REGS_CONV = 120;
 
 struct PipeParams {
   MlpDev mlp;
@@ -69,6 +70,7 @@ struct PipeParams {
   float* xchg; unsigned* flags;
   float* park;                       // integrators' parked states: [grid][PIPE_MAX_MT][DS_T/4 + 1][128] float4
   uint32_t* trace; int xflags;
+  uint32_t* dbg;                     // host-mapped watchdog record (BBMPC_DEBUG=1), else nullptr
 };
 
 struct PipeSmem { uint32_t wring, aring, table, jobs, bars, tmem_slot, stats, conv, total; };
@@ -102,8 +104,13 @@ __device__ __forceinline__ float ldg_f32(const float* p) {   // volatile: stays 
   asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
+#ifndef PIPE_NO_SETMAXNREG
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+#else   // debugging build: every role at the launch-time register count (spills)
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() {}
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() {}
+#endif
 
 template <bool ON>
 struct PTracer {
@@ -212,7 +219,7 @@ __device__ __forceinline__ void pipe_convert(uint32_t taddr, int Npad, int N, in
 
 template <int DS_T, int DU_T, bool TR, int ACT_T>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __grid_constant__ PipeParams p) {
-  volatile uint32_t* const dbgp = nullptr;
+  volatile uint32_t* const dbgp = TR ? p.dbg : nullptr;   // watchdog records only in the debug / trace build
   extern __shared__ __align__(128) uint8_t smem[];
   const MlpDev& M = p.mlp;
   const int nL = M.n_layers, nM = M.n_members;
@@ -388,7 +395,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
                   if (three) { mma_ts(d, a0 + 24, b1, job.idesc, 1u); mma_ts(d, a0 + 16, b1 + job.lo_off16, job.idesc, 1u); }
                 }
               } else {
-                if (!pre_ok) mbar_wait_poll(bar_afull + 8 * pu, wrap & 1u);
+                if (!pre_ok) mbar_wait_poll(bar_afull + 8 * pu, wrap & 1u, dbgp, 0x2000000u | (j << 12) | (l << 8) | u);
                 {  // probe the next unit before this unit's MMAs are issued (hides the probe latency)
                   uint32_t pn = pu + 1, wn = wrap;
                   if (pn == static_cast<uint32_t>(p.a_units)) { pn = 0; ++wn; }
@@ -569,7 +576,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
           unsigned seen = 0, spins = 0;
           do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.flags + xi) : "memory");
-            if (++spins > (1u << 24)) asm volatile("trap;");
+            if (++spins > (1u << 22)) {
+              if (dbgp && lane == 0) { dbgp[8 * warp] = 0xF1A60000u | threadIdx.x; dbgp[8 * warp + 1] = xi; dbgp[8 * warp + 2] = seen; dbgp[8 * warp + 3] = target; __threadfence_system(); }
+              asm volatile("trap;");
+            }
           } while (seen < target);
           tr.rec(0x41u);
           const float* base = p.xchg + ((static_cast<size_t>(xi) * 2 + (t & 1)) * nM) * (DS_T * PIPE_ROWS) + static_cast<size_t>(row_in_tile) * DS_T;
@@ -733,7 +743,7 @@ template <int DS_T, int DU_T>
 static int pipe_launch_t(bbmpc_ctx* ctx, const PipeParams& p, int grid, size_t smem_bytes, bool coop, cudaStream_t st) {
   bool all_tanh = !(p.xflags & 2);
   for (int l = 0; l + 1 < p.mlp.n_layers; ++l) all_tanh = all_tanh && p.mlp.layer[l].act == BBMPC_ACT_TANH;
-  auto kern = p.trace ? (all_tanh ? rollout_pipe_kernel<DS_T, DU_T, true, BBMPC_ACT_TANH> : rollout_pipe_kernel<DS_T, DU_T, true, -1>)
+  auto kern = (p.trace || p.dbg) ? (all_tanh ? rollout_pipe_kernel<DS_T, DU_T, true, BBMPC_ACT_TANH> : rollout_pipe_kernel<DS_T, DU_T, true, -1>)
                       : (all_tanh ? rollout_pipe_kernel<DS_T, DU_T, false, BBMPC_ACT_TANH> : rollout_pipe_kernel<DS_T, DU_T, false, -1>);
   BB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
   if (coop) {
@@ -745,6 +755,19 @@ static int pipe_launch_t(bbmpc_ctx* ctx, const PipeParams& p, int grid, size_t s
     kern<<<grid, PIPE_THREADS, smem_bytes, st>>>(p);
   }
   BB_LAUNCH_CHECK(ctx);
+  if (p.dbg) {  // BBMPC_DEBUG=1: synchronise and dump the watchdog record of a starved pipeline
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      const uint32_t* h = static_cast<const uint32_t*>(ctx->dbg_host);
+      for (int b = 0; b < 2; ++b)
+        for (int w = 0; w < PIPE_WARPS; ++w) {
+          const uint32_t* r = h + 256 * b + 8 * w;
+          if (r[0]) fprintf(stderr, "[bbmpc pipe watchdog] blk%%2=%d warp=%d tid=%u bar=+%u parity=%u tag=%08x\n", b, w, r[0] & 0xFFFF,
+                            r[1] - 0u, r[2], r[3]);
+        }
+      return fail(ctx, BBMPC_ECUDA, "rollout_pipe_kernel: %s", cudaGetErrorString(e));
+    }
+  }
   if (p.trace) {
     cudaStreamSynchronize(st);
     static std::vector<uint32_t> h(32 * 1024);
@@ -813,6 +836,13 @@ int launch_rollout_pipe(bbmpc_ctx* ctx, const float* states, const float* action
     static uint32_t* tbuf = nullptr;
     if (!tbuf) { BB_CUDA(ctx, cudaMalloc(&tbuf, 32 * 1024 * 4)); BB_CUDA(ctx, cudaMemset(tbuf, 0, 32 * 1024 * 4)); }
     p.trace = tbuf;
+  }
+  if (getenv("BBMPC_DEBUG")) {
+    if (!ctx->dbg_host) {
+      BB_CUDA(ctx, cudaHostAlloc(&ctx->dbg_host, 4096, cudaHostAllocMapped));
+      memset(ctx->dbg_host, 0, 4096);
+    }
+    BB_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void**>(&p.dbg), ctx->dbg_host, 0));
   }
   const int nM = m.mlp.n_members;
   const long long ids = static_cast<long long>(p.n_tiles) * nM;

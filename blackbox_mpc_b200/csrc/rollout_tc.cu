@@ -726,7 +726,7 @@ static int launch_t(bbmpc_ctx* ctx, const TcParams& p, int grid, size_t smem_byt
       uint32_t* h = static_cast<uint32_t*>(ctx->dbg_host);
       for (int b = 0; b < 2; ++b)
         for (int w = 0; w < TC_WARPS; ++w) {
-          const uint32_t* r = h + 128 * b + 8 * w;
+          const uint32_t* r = h + 256 * b + 8 * w;
           if (r[0]) fprintf(stderr, "[bbmpc watchdog] blk%%2=%d warp=%d tid=%u bar=+%u parity=%u tag=%08x\n", b, w, r[0] & 0xFFFF,
                             r[1], r[2], r[3]);
         }
@@ -786,8 +786,8 @@ static int launch_rollout_tc_once(bbmpc_ctx* ctx, const float* states, const flo
   }
   if (getenv("BBMPC_DEBUG")) {
     if (!ctx->dbg_host) {
-      BB_CUDA(ctx, cudaHostAlloc(&ctx->dbg_host, 1024, cudaHostAllocMapped));
-      memset(ctx->dbg_host, 0, 1024);
+      BB_CUDA(ctx, cudaHostAlloc(&ctx->dbg_host, 4096, cudaHostAllocMapped));
+      memset(ctx->dbg_host, 0, 4096);
     }
     BB_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void**>(&p.dbg), ctx->dbg_host, 0));
   }

@@ -57,7 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatil
   while (!mbar_try_wait(bar, parity)) {
     ++spins;
     if (dbg && spins == TC05_WATCHDOG_SPINS / 2 && (threadIdx.x & 31) == 0) {
-      const uint32_t slot = 8u * (threadIdx.x >> 5) + 128u * (blockIdx.x & 1);
+      const uint32_t slot = 8u * (threadIdx.x >> 5) + 256u * (blockIdx.x & 1);
       dbg[slot + 0] = 0xDEAD0000u | threadIdx.x; dbg[slot + 1] = bar; dbg[slot + 2] = parity; dbg[slot + 3] = tag;
       __threadfence_system();
     }

@@ -26,9 +26,18 @@ __device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity
 // Busy-polling wait (non-blocking test_wait): a suspended try_wait wakes up ~500 cycles after the phase
 // completes (measured with the in-kernel tracer); a single polling warp on the critical path reacts within
 // one probe latency (~100 cycles) at the price of a few issue slots.
-__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity, volatile uint32_t* dbg = nullptr, uint32_t tag = 0) {
   uint32_t spins = 0;
-  while (!mbar_test_wait(bar, parity)) { if (++spins > (1u << 26)) asm volatile("trap;"); }
+  while (!mbar_test_wait(bar, parity)) {
+    if (++spins > (1u << 25)) {
+      if (dbg) {
+        const uint32_t slot = 8u * (threadIdx.x >> 5) + 256u * (blockIdx.x & 1);
+        dbg[slot + 0] = 0xDEAD0000u | threadIdx.x; dbg[slot + 1] = bar; dbg[slot + 2] = parity; dbg[slot + 3] = tag;
+        __threadfence_system();
+      }
+      asm volatile("trap;");
+    }
+  }
 }
 
 // tanh of two pre-activations that arrive PRE-SCALED by 2 log2(e) (the scale is folded into the

@@ -226,3 +226,14 @@ class OptimizerBase:
         self._trace = torch.zeros(n_iters, per_iter, dtype=torch.float32, device=e.device)
         e.check(e.lib.bbmpc_opt_set_sample_trace(self._handle, _lib.ptr(self._trace), self._trace.numel()))
         return self._trace
+
+    def set_draw_injection(self, std_draws: Optional[torch.Tensor]) -> None:
+        """Test hook: feed the samplers STANDARD variates (one [P, A, H*dU] block per optimizer iteration) instead of
+        Philox (bbmpc_opt_set_draw_injection); None switches back.  The tensor is kept alive by the optimizer."""
+        e = self._ensure_handle()
+        if std_draws is None:
+            self._inject = None
+            e.check(e.lib.bbmpc_opt_set_draw_injection(self._handle, None, 0))
+            return
+        self._inject = std_draws.to(device=e.device, dtype=torch.float32).contiguous()
+        e.check(e.lib.bbmpc_opt_set_draw_injection(self._handle, _lib.ptr(self._inject), self._inject.numel()))

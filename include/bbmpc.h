@@ -188,6 +188,11 @@ int bbmpc_opt_p2p_connect(bbmpc_opt* opt, const void* handles_host, void* const*
  * Copies min(n_floats, size) floats into out (device) and returns the tensor's size in floats. */
 int64_t bbmpc_opt_get_tensor(bbmpc_opt* opt, const char* name, float* out, int64_t n_floats,
                              void* stream);
+/* Test hook (tests/test_gpu_golden.py): replace the optimizer's in-kernel Philox draws by injected STANDARD variates
+ * (truncated-normal z for CEM / PI2, U[0,1) for RandomSearch, +-1 for SPSA, N(0,1) for CMA-ES), fp32 on the device,
+ * one block of [population_size, num_agents, H*dU] floats (CMA-ES: [population_size, A*H*dU]) per optimizer
+ * iteration since this call, indexed by GLOBAL population row.  NULL switches back to Philox.  Not available for PSO. */
+int bbmpc_opt_set_draw_injection(bbmpc_opt* opt, const float* std_draws, int64_t n_floats);
 /* When set (device buffer of n_iters*P_local*A*H*dU floats), every iteration's evaluated samples
  * are also recorded there, so a test can inject the exact draws into the oracle.  NULL disables.
  * CMA-ES records its raw N(0,1) draws z [P_local, N] per iteration instead (the samples follow from z

@@ -48,6 +48,19 @@ def rollout_case(name, P, A, H, seed):
     return dict(actions=actions, returns=returns, next_state=nxt.numpy(), reward=rew.numpy())
 
 
+def rollout_full_case(name, P, seed):
+    """BASELINE-size rollout: the actions come from the seeded torch generator the GPU tests use
+    (tests/helpers.random_actions), so only the float64 returns and a checksum of the actions are stored."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    w = workloads.make(name, population_size=P, bias_scale=0.1)
+    actions = helpers.random_actions(w, P, seed=seed)
+    ev = ob.evaluator(w, F64)
+    returns = ev(torch.from_numpy(w.state).double(), actions.double(), 0).numpy()
+    return dict(returns=returns, actions_checksum=np.array([actions.double().sum().item(), actions.double().abs().sum().item()]),
+                seed=np.array([seed]))
+
+
 class RecordingDraws:
     """numpy-rng draws with TF sampler semantics; records the *standard* variates so a test can
     re-inject them."""
@@ -60,11 +73,20 @@ class RecordingDraws:
         self.rec.setdefault(tag, []).append(v32)  # re-injecting the stored draws reproduces the run
         return torch.from_numpy(v32).to(v.dtype)
 
+    # The STANDARD variate behind every affine draw is rounded to fp32 first and recorded as "std.<tag>": the GPU
+    # tests inject exactly these into the CUDA samplers (bbmpc_opt_set_draw_injection), tests/test_gpu_golden.py.
+    def _std(self, tag, v):
+        v32 = np.asarray(v).astype(np.float32)
+        self.rec.setdefault("std." + tag, []).append(v32)
+        return torch.from_numpy(v32.astype(np.float64))
+
     def truncated_normal(self, shape, mean, std, tag=""):
-        return self._keep(tag, mean + std * torch.from_numpy(std_truncnorm(tuple(shape), self.rng)).to(mean.dtype))
+        z = self._std(tag, std_truncnorm(tuple(shape), self.rng))
+        return self._keep(tag, mean + std * z.to(mean.dtype))
 
     def uniform(self, shape, lo, hi, tag=""):
-        return self._keep(tag, lo + (hi - lo) * torch.from_numpy(self.rng.random(tuple(shape))).to(lo.dtype))
+        u = np.minimum(self.rng.random(tuple(shape)), 1.0 - 2.0 ** -24)   # stays < 1 after the fp32 rounding
+        return self._keep(tag, lo + (hi - lo) * self._std(tag, u).to(lo.dtype))
 
     def normal(self, shape, tag=""):
         return self._keep(tag, torch.from_numpy(np.asarray(self.rng.standard_normal(tuple(shape)))).to(F64))
@@ -96,6 +118,8 @@ def main():
         "rollout_c2": rollout_case("C2", 48, 2, 30, 2),
         "rollout_c3": rollout_case("C3", 32, 1, 30, 3),
         "rollout_c4": rollout_case("C4", 24, 1, 30, 4),
+        "rollout_c4_full": rollout_full_case("C4", 10000, 31),
+        "rollout_c3_full": rollout_full_case("C3", 5000, 32),
         "opt_cem_c2": optimizer_case("C2", "CEM", 64, 2, 12, 5, max_iterations=3),
         "opt_pi2_c2": optimizer_case("C2", "PI2", 64, 2, 12, 6, max_iterations=3),
         "opt_rs_c1": optimizer_case("C1", "RandomSearch", 64, 2, 12, 7),

@@ -1,0 +1,88 @@
+"""GPU parity against the COMMITTED golden vectors (tests/golden/*.npz, written by tests/golden/make_golden.py from the
+float64 restatement of the reference): the CUDA path gets the stored inputs through the Python plugin classes (C ABI
+underneath) and must reproduce the stored outputs.  Nothing here runs the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from blackbox_mpc_b200.utils import workloads
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# (workload, P, A, H) of each fixture: must match tests/golden/make_golden.py
+ROLLOUT_CASES = {"rollout_c1": ("C1", 64, 1, 30), "rollout_c2": ("C2", 48, 2, 30), "rollout_c3": ("C3", 32, 1, 30),
+                 "rollout_c4": ("C4", 24, 1, 30)}
+TOL = {"fp32": dict(atol=2e-3, rtol=2e-5), "bf16x3": dict(atol=3e-3, rtol=3e-5)}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("fixture", sorted(ROLLOUT_CASES))
+def test_rollout_reproduces_golden_returns(cuda_device, fixture, precision):
+    name, P, A, H = ROLLOUT_CASES[fixture]
+    if name == "C1" and precision != "fp32":
+        pytest.skip("analytical pendulum dynamics has no tensor-core path")
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    w = workloads.make(name, population_size=P, planning_horizon=H, num_agents=A, bias_scale=0.1)
+    policy = workloads.build_policy(w, precision=precision)
+    ev = policy._trajectory_evaluator
+    assert ev.engine().effective_precision == precision
+    state = torch.from_numpy(w.state)
+    got = ev(state, torch.from_numpy(g["actions"]), 0).cpu().numpy()
+    assert got.shape == g["returns"].shape
+    helpers.compare_returns(got, g["returns"], max_jump_frac=0.05, **TOL[precision])
+    # single-step entry points on the first action of row 0 (predict_next_state / evaluate_next_reward)
+    a0 = torch.from_numpy(g["actions"][0, :, 0])
+    nxt = ev.predict_next_state(state, a0).cpu().numpy()
+    np.testing.assert_allclose(nxt, g["next_state"], rtol=2e-5, atol=2e-5)
+    rew = ev.evaluate_next_reward(state, torch.from_numpy(g["next_state"].astype(np.float32)), a0).cpu().numpy()
+    helpers.compare_returns(rew, g["reward"], atol=2e-3, rtol=2e-5, max_jump_frac=0.5)
+
+
+@pytest.mark.parametrize("fixture,name,P,seed", [("rollout_c4_full", "C4", 10000, 31), ("rollout_c3_full", "C3", 5000, 32)])
+def test_full_size_rollout_reproduces_golden_returns(cuda_device, fixture, name, P, seed):
+    """BASELINE population sizes (C4: 10 000 x 5 members, C3: 5 000) on the tensor-core path against committed float64
+    returns; the actions are regenerated from the seeded CPU generator and checked against the stored checksum."""
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    w = workloads.make(name, population_size=P, bias_scale=0.1)
+    actions = helpers.random_actions(w, P, seed=seed)
+    chk = np.array([actions.double().sum().item(), actions.double().abs().sum().item()])
+    np.testing.assert_allclose(chk, g["actions_checksum"], rtol=1e-12)
+    policy = workloads.build_policy(w, precision="bf16x3")
+    got = policy._trajectory_evaluator(torch.from_numpy(w.state), actions, 0).cpu().numpy()
+    helpers.compare_returns(got, g["returns"], max_jump_frac=0.02, **TOL["bf16x3"])
+
+
+# fixture -> (workload, optimizer, P, A, H, tag of the standard variates, ctor overrides): tests/golden/make_golden.py
+OPT_CASES = {
+    "opt_cem_c2": ("C2", "CEM", 64, 2, 12, "draws.std.cem.samples", dict(max_iterations=3, num_elite=16, alpha=0.25)),
+    "opt_pi2_c2": ("C2", "PI2", 64, 2, 12, "draws.std.pi2.samples", dict(max_iterations=3)),
+    "opt_rs_c1": ("C1", "RandomSearch", 64, 2, 12, "draws.std.rs.samples", dict()),
+    "opt_spsa_c2": ("C2", "SPSA", 32, 1, 12, "draws.spsa.delta", dict(max_iterations=3)),
+    "opt_cmaes_c2": ("C2", "CMA-ES", 48, 1, 8, "draws.cmaes.z", dict(max_iterations=3, num_elite=12)),
+}
+
+
+@pytest.mark.parametrize("fixture", sorted(OPT_CASES))
+def test_optimizer_reproduces_golden_actions(cuda_device, fixture):
+    """Whole act() on the CUDA path (sampler arithmetic -> rollout -> refit -> executed-action tail) fed with the
+    committed standard variates must land on the committed actions / next states / rewards of two consecutive calls
+    (the second call exercises the warm start)."""
+    name, opt_name, P, A, H, tag, over = OPT_CASES[fixture]
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    w = workloads.make(name, population_size=P, planning_horizon=H, num_agents=A, bias_scale=0.1)
+    w.optimizer_name, w.optimizer_args = opt_name, {k: v for k, v in over.items() if k != "max_iterations"}
+    if "max_iterations" in over:
+        w.max_iterations = over["max_iterations"]
+    policy = workloads.build_policy(w, precision="fp32")
+    opt = policy._optimizer
+    opt.set_draw_injection(torch.from_numpy(g[tag]))
+    state = torch.from_numpy(w.state)
+    for call in range(2):
+        action, nxt, rew = opt(state, call, False)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(action.cpu().numpy(), g[f"action{call}"], rtol=2e-4, atol=2e-4, err_msg=f"action, call {call}")
+        np.testing.assert_allclose(nxt.cpu().numpy(), g[f"next{call}"], rtol=2e-4, atol=2e-4, err_msg=f"next state, call {call}")
+        helpers.compare_returns(rew.cpu().numpy(), g[f"reward{call}"], atol=2e-3, rtol=2e-4, max_jump_frac=0.5)

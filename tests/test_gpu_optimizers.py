@@ -72,33 +72,77 @@ def test_other_optimizers_match_oracle(cuda_device, opt_name):
 
 
 def test_pso_matches_oracle(cuda_device):
-    w = workloads.make("C2", population_size=200, num_agents=2, bias_scale=0.1)
+    """optimizers/pso.py:79-138 step by step: the CUDA swarm is driven through begin / iter_local / iter_merge / finish
+    and its x, v, personal and global bests are compared with the float64 oracle after EVERY iteration, with the same
+    initial swarm, the same (r1, r2) scalars (read back through get_tensor("pso_r")) and, for the tail, the CUDA
+    path's own re-seed draws injected into the oracle.  A second act() call then runs on the re-seeded swarm."""
+    from blackbox_mpc_b200 import _lib
+    P, A = 200, 2
+    w = workloads.make("C2", population_size=P, num_agents=A, bias_scale=0.1)
     policy = workloads.build_policy(w, precision="fp32", optimizer_name="PSO")
     opt = policy._optimizer
     opt.reset()
-    x0 = opt.get_tensor("x").cpu().reshape(200, 2, w.planning_horizon, w.dU)
-    v0 = opt.get_tensor("v").cpu().reshape_as(x0)
+    e, lib, h = opt._ensure_handle(), opt._engine.lib, opt._handle
+    shape = (P, A, w.planning_horizon, w.dU)
     lb, ub = torch.from_numpy(w.lb), torch.from_numpy(w.ub)
+    state = torch.from_numpy(w.state).to(e.device)
+    n_iters = lib.bbmpc_opt_num_iterations(h)
+    o = helpers.oracle_optimizer(w, "PSO", dtype=torch.float64)
+    get = lambda name, shp: opt.get_tensor(name).cpu().reshape(shp).double()   # noqa: E731
+    x0, v0 = get("x", shape), get("v", shape)
     assert (x0 >= lb).all() and (x0 <= ub).all() and (v0.abs() <= 0.01 * (ub - lb) + 1e-7).all()
-    action, nxt, rew = opt(torch.from_numpy(w.state), 0, False)
-    torch.cuda.synchronize()
-    # oracle with the same initial swarm; r1/r2 and the re-seed draws cannot be injected from the
-    # outside, so compare the first iteration's personal/global best bookkeeping instead
-    o = helpers.oracle_optimizer(w, "PSO", dtype=torch.float64, max_iterations=1)
-    o._x, o._v, o._pbest_x = x0.double(), v0.double(), x0.double()
-    o._pbest_r = torch.full((200, 2), -float("inf"), dtype=torch.float64)
+    o._x, o._v, o._pbest_x = x0.clone(), v0.clone(), x0.clone()
+    o._pbest_r = torch.full((P, A), -float("inf"), dtype=torch.float64)
+    o._gbest_r = torch.full((A,), -float("inf"), dtype=torch.float64)
 
-    class D(oracle.TorchDraws):
-        pass
-    o(torch.from_numpy(w.state).double(), 0, False, D(0, torch.float64))
-    # after one oracle iteration gbest == argmax of plain rollout returns of x0
-    ev = policy._trajectory_evaluator
-    r0 = ev(torch.from_numpy(w.state), x0, 0).cpu()
-    best = r0.argmax(dim=0)
-    for a in range(2):
-        np.testing.assert_allclose(o.trace[0]["gbest_x"][a].numpy(), x0[best[a], a].numpy(), rtol=0, atol=1e-6)
-    action = action.cpu()
-    assert torch.isfinite(action).all() and (action >= lb).all() and (action <= ub).all()
+    for call in range(2):
+        # ---- CUDA path, one iteration at a time
+        e.check(lib.bbmpc_opt_begin(h, _lib.ptr(state), call, None))
+        cuda_iters = []
+        for it in range(n_iters):
+            e.check(lib.bbmpc_opt_iter_local(h, it, None, None))
+            e.check(lib.bbmpc_opt_iter_merge(h, it, None, 1, None))
+            torch.cuda.synchronize()
+            cuda_iters.append(dict(x=get("x", shape), v=get("v", shape), pbx=get("pbest_x", shape), pbr=get("pbest_r", (P, A)),
+                                   gbx=get("gbest_x", shape[1:]), gbr=get("gbest_r", (A,))))
+        r12 = opt.get_tensor("pso_r").cpu().double()[: 2 * n_iters].reshape(n_iters, 2)
+        gb_final = cuda_iters[-1]["gbx"]
+        act = torch.empty(A, w.dU, device=e.device)
+        nxt = torch.empty(A, w.dS, device=e.device)
+        e.check(lib.bbmpc_opt_finish(h, 0, _lib.ptr(act), _lib.ptr(nxt), None, None))
+        torch.cuda.synchronize()
+        x_seed, v_seed = get("x", shape), get("v", shape)
+        # ---- oracle with the same scalars and the CUDA path's re-seed draws
+        draws = oracle.InjectedDraws({"pso.r1": [r12[i, 0].reshape(()) for i in range(n_iters)],
+                                      "pso.r2": [r12[i, 1].reshape(()) for i in range(n_iters)],
+                                      "pso.reseed_x": [x_seed], "pso.reseed_v": [v_seed]}, dtype=torch.float64)
+        ref_action, ref_next, _ = o(torch.from_numpy(w.state).double(), call, False, draws)
+        assert len(o.trace) == n_iters
+        for it, (c, r) in enumerate(zip(cuda_iters, o.trace)):
+            msg = f"act() call {call}, iteration {it}"
+            np.testing.assert_allclose(c["x"].numpy(), r["x"].numpy(), rtol=1e-4, atol=2e-5, err_msg="x, " + msg)
+            np.testing.assert_allclose(c["v"].numpy(), r["v"].numpy(), rtol=1e-4, atol=2e-5, err_msg="v, " + msg)
+            np.testing.assert_allclose(c["gbx"].numpy(), r["gbest_x"].numpy(), rtol=1e-4, atol=2e-5, err_msg="gbest_x, " + msg)
+            best_rows = r["best"]
+            for a in range(A):   # the global best IS the personal best of the arg-max particle (pso.py:97-103)
+                np.testing.assert_allclose(c["pbx"][best_rows[a], a].numpy(), c["gbx"][a].numpy(), rtol=0, atol=0)
+                assert c["gbr"][a] == c["pbr"][:, a].max()
+            # personal bests: monotone, and equal to the best clipped position seen so far
+            if it > 0:
+                assert (c["pbr"] >= cuda_iters[it - 1]["pbr"]).all()
+        np.testing.assert_allclose(act.cpu().numpy(), ref_action.numpy(), rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(nxt.cpu().numpy(), ref_next.numpy(), rtol=2e-4, atol=2e-4)
+        # ---- the tail (pso.py:114-138): re-seed support and bookkeeping
+        H, dU = w.planning_horizon, w.dU
+        g = gb_final                                           # [A, H, dU]
+        shifted = torch.cat([g[:, 1:], g[:, -1:]], dim=1)
+        var0 = ((ub - lb).double() / 4.0) ** 2                 # optimizer_base.py:44-46 solution variance
+        cvar = torch.minimum(torch.minimum(((g - lb) / 2) ** 2, ((ub - g) / 2) ** 2), var0.expand_as(g))
+        assert ((x_seed - shifted).abs() <= 2.0 * cvar.sqrt() + 1e-6).all(), "re-seeded positions outside +-2 sigma of shift(gbest)"
+        assert (v_seed.abs() <= 0.01 * (ub - lb) + 1e-7).all()
+        assert torch.equal(get("pbest_x", shape), x_seed)
+        assert torch.isinf(get("pbest_r", (P, A))).all() and torch.isinf(get("gbest_r", (A,))).all()
+        assert (x_seed[:, :, :, :].std(dim=0) > 0).any()
 
 
 def test_mpc_policy_act_marshalling(cuda_device):
