@@ -179,7 +179,7 @@ def test_oracle_reproduces_golden_optimizer_runs(case, wname, opt_name, P, A, H,
 
 
 def test_golden_fixture_inventory():
-    assert len(glob.glob(os.path.join(GOLDEN, "*.npz"))) == 9
+    assert len(glob.glob(os.path.join(GOLDEN, "*.npz"))) == 11   # 4 rollouts + 2 full-size return vectors + 5 optimizer runs
     assert os.path.exists(os.path.join(GOLDEN, "make_golden.py"))
 
 
