@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libbbmpc.so")
 OBJ_DIR = os.path.join(CSRC, "build")
-SOURCES = ["context.cu", "rollout_simt.cu", "rollout_tc.cu", "rollout_pipe.cu", "optimizers.cu", "cmaes.cu"]
+SOURCES = ["context.cu", "rollout_simt.cu", "rollout_tc.cu", "rollout_pipe.cu", "optimizers.cu", "cmaes.cu", "user_reward.cu"]
 HEADERS = ["common.cuh", "device_fns.cuh", "tc05.cuh", "tc_epi.cuh", "pipe_sched.h", "refit.cuh", "opt_state.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

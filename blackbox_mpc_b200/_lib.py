@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("BBMPC_LIB") or os.path.join(_HERE, "libbbmpc.so")   #
 # mirrors of include/bbmpc.h
 OK, EINVAL, ECUDA, ESTATE, ENOMEM = 0, -1, -2, -3, -4
 DYN_MLP, DYN_PENDULUM = 0, 1
-REWARD_PENDULUM, REWARD_HALFCHEETAH, REWARD_PENDULUM_GYM = 1, 2, 3
+REWARD_PENDULUM, REWARD_HALFCHEETAH, REWARD_PENDULUM_GYM, REWARD_USER = 1, 2, 3, 4
 ACT_NONE, ACT_TANH, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 PREC_AUTO, PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2, 3
 OPT_CEM, OPT_PI2, OPT_RANDOM_SEARCH, OPT_PSO, OPT_SPSA, OPT_CMAES = 1, 2, 3, 4, 5, 6
@@ -51,6 +51,7 @@ SIGNATURES = {
     "bbmpc_model_set_norm": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "bbmpc_model_set_builtin": (_I, [_VP, _I, _I, _I]),
     "bbmpc_reward_set_builtin": (_I, [_VP, _I]),
+    "bbmpc_reward_set_nvrtc": (_I, [_VP, C.c_char_p]),
     "bbmpc_rollout": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "bbmpc_predict_next_state": (_I, [_VP, _VP, _VP, _VP, _I, _VP]),
     "bbmpc_reward": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _VP]),

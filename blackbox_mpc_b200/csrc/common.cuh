@@ -118,6 +118,11 @@ struct bbmpc_ctx {
   unsigned* tc_flags = nullptr; int tc_flags_n = 0;
   float* pipe_park = nullptr; size_t pipe_park_floats = 0;   // pipelined rollout: parked member-tile states
   bool tc_no_groups = false;   // a cooperative launch did not fit: stay with one CTA per tile
+  // user reward compiled with NVRTC (user_reward.cu): loaded library, its two kernels, the source it was built from
+  void* user_reward_lib = nullptr; cudaKernel_t user_reward_traj = nullptr; cudaKernel_t user_reward_rows = nullptr;
+  int user_reward_dS = 0, user_reward_dU = 0; std::string user_reward_src;
+  float* traj_buf = nullptr; size_t traj_floats = 0;   // visited states of the current rollout [rows][H][dS]
+  float* traj_cur = nullptr;                             // non-null while a rollout must dump its states
   void* dbg_host = nullptr;  // BBMPC_DEBUG=1: host-mapped watchdog record of the tensor-core kernel
   // rollout-kernel timing (bbmpc_profile_*): event pairs recorded around every rollout launch
   bool prof_on = false;
@@ -165,6 +170,12 @@ uint32_t tc_idesc(int Npad);  // instruction descriptor of the rollout kernel's 
 bool tc_column_map(const MlpDev& m, int* buf_w, int* col_x, int* col_dout);  // TMEM budget of the rollout kernel
 int tc_du_slots(int dU);  // action slots at the head of the layer-0 K axis (8 or 16)
 int resolve_precision(const bbmpc_ctx* ctx);
+// user rewards (user_reward.cu)
+void user_reward_free(bbmpc_ctx* ctx);
+int user_reward_traj_buffer(bbmpc_ctx* ctx, int rows, int H, cudaStream_t st, float** out);
+int launch_user_reward_traj(bbmpc_ctx* ctx, const float* traj, const float* states, const float* actions, const float* penalty,
+                            float* returns, int rows, int A, int H, cudaStream_t st);
+int launch_user_reward_rows(bbmpc_ctx* ctx, const float* s, const float* a, const float* s2, float* out, int B, cudaStream_t st);
 // rollout dispatch used by bbmpc_rollout and the optimizers.  `penalty` (nullable, [rows]) is
 // subtracted from the return before the NaN guard is applied?  No: the reference applies the NaN
 // guard inside the evaluator and subtracts the penalty outside, so penalty is subtracted AFTER.

@@ -133,6 +133,11 @@ int rollout_dispatch(bbmpc_ctx* ctx, const float* states, const float* actions, 
     BB_CUDA(ctx, cudaEventRecord(e0, st));
   }
   int rc;
+  // user reward: the kernels dump the visited states (their own reward is off), a JIT-compiled kernel sums the reward
+  const bool user_reward = ctx->reward_id == BBMPC_REWARD_USER;
+  ctx->traj_cur = nullptr;
+  if (user_reward && H > 0)
+    if (int rc2 = user_reward_traj_buffer(ctx, rows, H, st, &ctx->traj_cur)) return rc2;
   if (prec == BBMPC_PREC_FP32)
     rc = launch_rollout_simt(ctx, states, actions, returns, penalty, rows, A, H, 0, st);
   else {
@@ -144,6 +149,9 @@ int rollout_dispatch(bbmpc_ctx* ctx, const float* states, const float* actions, 
     if (H > 0 && !(pipe_env && pipe_env[0] == '0')) rc = launch_rollout_pipe(ctx, states, actions, returns, penalty, rows, A, H, passes, st);
     if (rc == -100) rc = launch_rollout_tc(ctx, states, actions, returns, penalty, rows, A, H, passes, st);
   }
+  if (rc == BBMPC_OK && user_reward)
+    rc = launch_user_reward_traj(ctx, ctx->traj_cur, states, actions, penalty, returns, rows, A, H, st);
+  ctx->traj_cur = nullptr;
   if (rc == BBMPC_OK && e1) {
     BB_CUDA(ctx, cudaEventRecord(e1, st));
     ctx->prof_n++;
@@ -194,6 +202,7 @@ void bbmpc_ctx_destroy(bbmpc_ctx* ctx) {
   cudaFree(ctx->model.norm_buf);
   cudaFree(ctx->step_scratch); cudaFree(ctx->step_counters);
   cudaFree(ctx->tc_xchg); cudaFree(ctx->tc_flags); cudaFree(ctx->pipe_park);
+  user_reward_free(ctx);
   if (ctx->dbg_host) cudaFreeHost(ctx->dbg_host);
   for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
   delete ctx;
@@ -464,6 +473,9 @@ int bbmpc_reward_set_builtin(bbmpc_ctx* ctx, int reward_id) {
 
 static int check_reward_dims(bbmpc_ctx* ctx) {
   const ModelHost& m = ctx->model;
+  if (ctx->reward_id == BBMPC_REWARD_USER && (ctx->user_reward_dS != m.dS || ctx->user_reward_dU != m.dU))
+    return fail(ctx, BBMPC_ESTATE, "the user reward was compiled for dS=%d dU=%d, the model has dS=%d dU=%d: set it again",
+                ctx->user_reward_dS, ctx->user_reward_dU, m.dS, m.dU);
   if (ctx->reward_id == BBMPC_REWARD_HALFCHEETAH && m.dS < 18)
     return fail(ctx, BBMPC_EINVAL, "HalfCheetah reward reads state[17]; dS=%d", m.dS);
   if ((ctx->reward_id == BBMPC_REWARD_PENDULUM || ctx->reward_id == BBMPC_REWARD_PENDULUM_GYM) && m.dS < 3)
@@ -498,6 +510,7 @@ int bbmpc_reward(bbmpc_ctx* ctx, const float* s, const float* a, const float* s2
   if (int rc = check_reward_dims(ctx)) return rc;
   if (B <= 0) return B == 0 ? BBMPC_OK : fail(ctx, BBMPC_EINVAL, "B < 0");
   BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->reward_id == BBMPC_REWARD_USER) return launch_user_reward_rows(ctx, s, a, s2, out, B, static_cast<cudaStream_t>(stream));
   StepIO io{s, a, s2, nullptr, out, nullptr, B, 2};
   return launch_step_simt(ctx, io, static_cast<cudaStream_t>(stream));
 }

@@ -68,6 +68,7 @@ struct PipeParams {
   int tiles_per_round, xchg_tiles;
   const TcJob* jobs; const uint2* table; int n_table;
   float* xchg; unsigned* flags;
+  float* traj;                       // user reward: visited states [rows][H][dS] (else nullptr)
   float* park;                       // integrators' parked states: [grid][PIPE_MAX_MT][DS_T/4 + 1][128] float4
   uint32_t* trace; int xflags;
   uint32_t* dbg;                     // host-mapped watchdog record (BBMPC_DEBUG=1), else nullptr
@@ -160,61 +161,82 @@ __device__ __forceinline__ void pconv_tail(const uint32_t (&r)[16], bool has_dat
   for (int j = 0; j < 8; ++j) split_bf16x2_veltkamp(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
 }
 
-// One hidden-layer conversion of one warp: chunks c = sub, sub+2, ... of its 32 TMEM lanes, software
-// pipelined (the load of the next chunk is in flight while the current one is converted).
+// One hidden-layer conversion of one warp: chunks c = sub, sub+2, ... of its 32 TMEM lanes.  Measured (ncu source
+// page, profiles/r2*): with two conversion warps per scheduler the loop is bound by the dependent-issue latency of
+// one chunk's tanh + hi/lo split (about 120 instructions, 300 cycles of fixed stalls), not by a pipe.  So a warp
+// converts TWO chunks per iteration (the compiler interleaves their eight quads: twice the instruction-level
+// parallelism), ring and barrier addresses advance by constants, and EVERY lane arrives on a unit's barrier after its
+// own stores and proxy fence (no warp-level sync or lane election on the way).
 template <int ACT, bool TR>
 __device__ __forceinline__ void pipe_convert(uint32_t taddr, int Npad, int N, int n_a_chunks, int sub, int passes,
                                             uint32_t aring, uint32_t chunk_bytes, uint32_t a_units, uint32_t pu, uint32_t wrap,
                                             uint32_t bar_afull, uint32_t bar_afree, uint32_t bar_drained, int row, int lane,
                                             const float* tail_tab, volatile uint32_t* dbgp, PTracer<TR>& tr) {
-  const int n_full = N >> 4;
-  uint32_t r[16];
-  int c = sub;
-  if (c < n_a_chunks && 16 * c < Npad) tmem_ld16(taddr + 16 * c, r);
-  bool drained = false;
-  for (; c < n_a_chunks; c += 2) {
-    tr.rec(0x100u | c);
-    wait_ld();
-    uint32_t cur[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) cur[j] = r[j];
-    const int cn = c + 2;
-    const bool more = cn < n_a_chunks && 16 * cn < Npad;
-    if (more) tmem_ld16(taddr + 16 * cn, r);
-    else if (!drained) {
-      // this warp's last read of the accumulator is complete: the D buffer may be overwritten
-      drained = true;
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_drained);
-    }
-    uint32_t hi[8], lo[8];
-    if (c < n_full) pconv_full<ACT>(cur, hi, lo);
-    else pconv_tail<ACT>(cur, 16 * c < Npad, tail_tab + 32 * (c - n_full), hi, lo);
-    // (pu, wrap): ring position of this chunk's unit
-    if (wrap > 0) mbar_wait(bar_afree + 8 * pu, (wrap - 1) & 1u, dbgp, 0x8000000u | (c << 8) | pu);
-    tr.rec(0x200u | c);
-    const uint32_t base = aring + (2 * pu + (c & 1)) * chunk_bytes + static_cast<uint32_t>(row) * 16;
-    st_shared_v4(base, hi[0], hi[1], hi[2], hi[3]);
-    st_shared_v4(base + PIPE_ROWS * 16, hi[4], hi[5], hi[6], hi[7]);
+  const int n_full = N >> 4;        // chunks whose 16 columns are all real features
+  const int n_data = Npad >> 4;     // chunks that carry accumulator data at all
+  const uint32_t unit_bytes = 2 * chunk_bytes;
+  uint32_t slot = aring + pu * unit_bytes + static_cast<uint32_t>(sub) * chunk_bytes + static_cast<uint32_t>(row) * 16;
+  uint32_t bf = bar_afull + 8 * pu;
+  const uint32_t bf_end = bar_afull + 8 * a_units, free_off = bar_afree - bar_afull;
+  auto store = [&](const uint32_t (&hi)[8], const uint32_t (&lo)[8], uint32_t at) {
+    st_shared_v4(at, hi[0], hi[1], hi[2], hi[3]);
+    st_shared_v4(at + PIPE_ROWS * 16, hi[4], hi[5], hi[6], hi[7]);
     if (passes == 3) {
-      st_shared_v4(base + 2 * PIPE_ROWS * 16, lo[0], lo[1], lo[2], lo[3]);
-      st_shared_v4(base + 3 * PIPE_ROWS * 16, lo[4], lo[5], lo[6], lo[7]);
+      st_shared_v4(at + 2 * PIPE_ROWS * 16, lo[0], lo[1], lo[2], lo[3]);
+      st_shared_v4(at + 3 * PIPE_ROWS * 16, lo[4], lo[5], lo[6], lo[7]);
     }
-    fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
-    __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(bar_afull + 8 * pu);
-      if ((c ^ 1) >= n_a_chunks) mbar_arrive(bar_afull + 8 * pu);   // lone last chunk stands for its missing partner
-    }
-    tr.rec(0x300u | c);
-    if (++pu == a_units) { pu = 0; ++wrap; }
-  }
-  if (!drained) {   // no chunk of this warp carried accumulator data
+  };
+  auto advance = [&]() {
+    slot += unit_bytes; bf += 8;
+    if (bf == bf_end) { slot -= a_units * unit_bytes; bf = bar_afull; ++wrap; }
+  };
+  auto drained = [&]() {   // this warp's last read of the accumulator is complete: the D buffer may be overwritten
     fence_before_sync();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_drained);
+  };
+  int c = sub;
+  // ---- pairs of full chunks
+  for (; c + 2 < n_full; c += 4) {
+    tr.rec(0x100u | c);
+    uint32_t ra[16], rb[16];
+    tmem_ld16(taddr + 16 * c, ra);
+    tmem_ld16(taddr + 16 * (c + 2), rb);
+    wait_ld();
+    if (c + 4 >= n_data) drained();
+    uint32_t hia[8], loa[8], hib[8], lob[8];
+    pconv_full<ACT>(ra, hia, loa);
+    pconv_full<ACT>(rb, hib, lob);
+    tr.rec(0x200u | c);
+    if (wrap > 0) mbar_wait_sleep(bf + free_off, (wrap - 1) & 1u, dbgp, 0x8000000u | (c << 8));
+    const uint32_t slot0 = slot, bf0 = bf;
+    store(hia, loa, slot0);
+    advance();
+    if (wrap > 0) mbar_wait_sleep(bf + free_off, (wrap - 1) & 1u, dbgp, 0x8100000u | (c << 8));
+    store(hib, lob, slot);
+    fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+    mbar_arrive(bf0);
+    if (((c + 2) ^ 1) < n_a_chunks) mbar_arrive(bf); else mbar_arrive_n(bf, 2);
+    advance();
+    tr.rec(0x300u | c);
   }
+  // ---- remaining chunks one at a time (at most one full chunk, then the trailing chunks with ones-columns / padding)
+  for (; c < n_a_chunks; c += 2) {
+    tr.rec(0x100u | c);
+    uint32_t r[16];
+    if (c < n_data) { tmem_ld16(taddr + 16 * c, r); wait_ld(); if (c + 2 >= n_data) drained(); }
+    uint32_t hi[8], lo[8];
+    if (c < n_full) pconv_full<ACT>(r, hi, lo);
+    else pconv_tail<ACT>(r, c < n_data, tail_tab + 32 * (c - n_full), hi, lo);
+    tr.rec(0x200u | c);
+    if (wrap > 0) mbar_wait_sleep(bf + free_off, (wrap - 1) & 1u, dbgp, 0x8200000u | (c << 8));
+    store(hi, lo, slot);
+    fence_proxy_async_smem();
+    if ((c ^ 1) < n_a_chunks) mbar_arrive(bf); else mbar_arrive_n(bf, 2);   // a lone last chunk stands for its missing partner
+    advance();
+    tr.rec(0x300u | c);
+  }
+  if (sub >= n_data) drained();   // no chunk of this warp carried accumulator data
 }
 
 template <int DS_T, int DU_T, bool TR, int ACT_T>
@@ -229,7 +251,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
   const TcJob* jobs = reinterpret_cast<const TcJob*>(smem + lay.jobs);
   const uint32_t bar_wfull = smem_base + lay.bars;
   const uint32_t bar_wempty = bar_wfull + PIPE_MAX_WSTAGES * 8;
-  const uint32_t bar_afull = bar_wempty + PIPE_MAX_WSTAGES * 8;    // conversion -> MMA: ring unit written (8 arrivals)
+  const uint32_t bar_afull = bar_wempty + PIPE_MAX_WSTAGES * 8;    // conversion -> MMA: ring unit written (256 arrivals: every lane of the 8 warps)
   const uint32_t bar_afree = bar_afull + PIPE_MAX_UNITS * 8;       // MMA -> conversion: ring unit consumed (commit)
   const uint32_t bar_dfull = bar_afree + PIPE_MAX_UNITS * 8;       // MMA -> conversion: hidden accumulator in D[b] complete
   const uint32_t bar_dout = bar_dfull + 16;                        // MMA -> publishers / integrators: output accumulator in D[b]
@@ -267,7 +289,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
   }
   if (tid == 0) {
     for (int s = 0; s < p.n_wstages; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
-    for (int u = 0; u < p.a_units; ++u) { mbar_init(bar_afull + 8 * u, 8); mbar_init(bar_afree + 8 * u, 1); }
+    for (int u = 0; u < p.a_units; ++u) { mbar_init(bar_afull + 8 * u, 256); mbar_init(bar_afree + 8 * u, 1); }   // 2 chunks x 4 quarters x 32 lanes
     for (int b = 0; b < 2; ++b) { mbar_init(bar_dfull + 8 * b, 1); mbar_init(bar_dout + 8 * b, 1); mbar_init(bar_drained + 8 * b, 8); }
     for (int i = 0; i < PIPE_MAX_MT; ++i) mbar_init(bar_xfull + 8 * i, 4);
     fence_mbar_init();
@@ -324,15 +346,19 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
           const int g0 = first_group[l], g1 = g0 + static_cast<int>(jobs[l].ngroups);
           for (int g = g0; g < g1; ++g) {
             const uint2 e = table[g];
-            mbar_wait(bar_wempty + 8 * stage, phase ^ 1, dbgp, 0x6000000u);
+            mbar_wait_sleep(bar_wempty + 8 * stage, phase ^ 1, dbgp, 0x6000000u);
             mbar_arrive_expect_tx(bar_wfull + 8 * stage, e.y);
             bulk_g2s(smem_base + lay.wring + stage * p.stage_bytes, wimg + e.x, e.y, bar_wfull + 8 * stage);
             if (++stage == static_cast<uint32_t>(p.n_wstages)) { stage = 0; phase ^= 1; }
           }
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ============================================================ MMA issuer (single thread)
+    } else if (warp == 1) {
+      // ============================================================ MMA issuer
+      // The whole warp runs the (warp-uniform) control flow and one elected lane issues the tcgen05 instructions of a
+      // unit back to back.  (A loop executed by a single lane makes ptxas wrap EVERY tcgen05.mma in an elect /
+      // broadcast / vote sequence of ~60 stall cycles that also waits for the previous MMA to read its operands:
+      // measured ~200 cycles per MMA instead of ~50, profiles/r2*.)
       const bool three = (p.passes == 3);
       uint32_t stage = 0, phase = 0;
       uint32_t useq = 0;                    // ring units allocated so far (mirrors the conversion warps)
@@ -352,7 +378,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
         int j, l, b;
         while (seq.next(j, l, b)) {
           const int i = j % n_mt;
-          tr.arm(p.trace && blockIdx.x == 0 && j / n_mt == 2);
+          tr.arm(p.trace && blockIdx.x == 0 && lane == 0 && j / n_mt == 2);
           const TcJob job = jobs[l];
           const uint32_t d = tmem_base + (b ? p.col_d1 : p.col_d0);
           {
@@ -386,14 +412,18 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
               const uint32_t blo = job.desc_lo_base | ((sbase + 2 * k * job.chunk16) & 0x3FFFu);
               const uint64_t b0 = (static_cast<uint64_t>(DESC_HI) << 32) | blo;
               if (l == 0) {
-                const uint32_t a0 = xcol + 32 * u;
-                mma_ts(d, a0, b0, job.idesc, acc);
-                if (three) { mma_ts(d, a0 + 8, b0, job.idesc, 1u); mma_ts(d, a0, b0 + job.lo_off16, job.idesc, 1u); }
-                if (two) {
-                  const uint64_t b1 = b0 + job.chunk16;
-                  mma_ts(d, a0 + 16, b1, job.idesc, 1u);
-                  if (three) { mma_ts(d, a0 + 24, b1, job.idesc, 1u); mma_ts(d, a0 + 16, b1 + job.lo_off16, job.idesc, 1u); }
+                fence_after_sync();
+                if (elect_one()) {
+                  const uint32_t a0 = xcol + 32 * u;
+                  mma_ts(d, a0, b0, job.idesc, acc);
+                  if (three) { mma_ts(d, a0 + 8, b0, job.idesc, 1u); mma_ts(d, a0, b0 + job.lo_off16, job.idesc, 1u); }
+                  if (two) {
+                    const uint64_t b1 = b0 + job.chunk16;
+                    mma_ts(d, a0 + 16, b1, job.idesc, 1u);
+                    if (three) { mma_ts(d, a0 + 24, b1, job.idesc, 1u); mma_ts(d, a0 + 16, b1 + job.lo_off16, job.idesc, 1u); }
+                  }
                 }
+                __syncwarp();
               } else {
                 if (!pre_ok) mbar_wait_poll(bar_afull + 8 * pu, wrap & 1u, dbgp, 0x2000000u | (j << 12) | (l << 8) | u);
                 {  // probe the next unit before this unit's MMAs are issued (hides the probe latency)
@@ -402,24 +432,29 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
                   pre_ok = (u + 1 < n_units) ? mbar_test_wait(bar_afull + 8 * pn, wn & 1u) : 0u;
                 }
                 fence_after_sync();
-                const uint32_t alo = a_desc_lo_base | ((aring16 + 2 * pu * achunk16) & 0x3FFFu);
-                const uint64_t a0 = (static_cast<uint64_t>(DESC_HI) << 32) | alo;
-                mma_ss(d, a0, b0, job.idesc, acc);
-                if (three) { mma_ss(d, a0 + a_lo_off16, b0, job.idesc, 1u); mma_ss(d, a0, b0 + job.lo_off16, job.idesc, 1u); }
-                if (two) {
-                  const uint64_t a1 = a0 + achunk16, b1 = b0 + job.chunk16;
-                  mma_ss(d, a1, b1, job.idesc, 1u);
-                  if (three) { mma_ss(d, a1 + a_lo_off16, b1, job.idesc, 1u); mma_ss(d, a1, b1 + job.lo_off16, job.idesc, 1u); }
+                if (elect_one()) {
+                  const uint32_t alo = a_desc_lo_base | ((aring16 + 2 * pu * achunk16) & 0x3FFFu);
+                  const uint64_t a0 = (static_cast<uint64_t>(DESC_HI) << 32) | alo;
+                  mma_ss(d, a0, b0, job.idesc, acc);
+                  if (three) { mma_ss(d, a0 + a_lo_off16, b0, job.idesc, 1u); mma_ss(d, a0, b0 + job.lo_off16, job.idesc, 1u); }
+                  if (two) {
+                    const uint64_t a1 = a0 + achunk16, b1 = b0 + job.chunk16;
+                    mma_ss(d, a1, b1, job.idesc, 1u);
+                    if (three) { mma_ss(d, a1 + a_lo_off16, b1, job.idesc, 1u); mma_ss(d, a1, b1 + job.lo_off16, job.idesc, 1u); }
+                  }
+                  mma_commit(bar_afree + 8 * pu);   // the unit may be refilled when these MMAs retire
                 }
-                mma_commit(bar_afree + 8 * pu);   // the unit may be refilled when these MMAs retire
+                __syncwarp();
                 if (++pu == static_cast<uint32_t>(p.a_units)) { pu = 0; ++wrap; }
               }
               acc = 1u;
             }
-            mma_commit(bar_wempty + 8 * stage);
+            if (elect_one()) mma_commit(bar_wempty + 8 * stage);
+            __syncwarp();
             if (++stage == static_cast<uint32_t>(p.n_wstages)) { stage = 0; phase ^= 1; }
           }
-          mma_commit((l + 1 < nL ? bar_dfull : bar_dout) + 8 * b);
+          if (elect_one()) mma_commit((l + 1 < nL ? bar_dfull : bar_dout) + 8 * b);
+          __syncwarp();
           tr.rec(0x1800u | (l << 8) | (b << 4));
         }
       }
@@ -444,7 +479,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
           const int i = j % n_mt, t = j / n_mt;
           tr.arm(p.trace && blockIdx.x == 0 && lane == 0 && t == 2);
           const int b = (n_mt == 1) ? b_single : (j & 1);
-          mbar_wait(bar_dout + 8 * b, (b ? oc1 : oc0) & 1u, dbgp, 0x5000000u | j);
+          mbar_wait_sleep(bar_dout + 8 * b, (b ? oc1 : oc0) & 1u, dbgp, 0x5000000u | j);
           if (b) ++oc1; else ++oc0;
           fence_after_sync();
           tr.rec(0x30u);
@@ -573,14 +608,22 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
         if (nM > 1) {
           const int xi = tile_i % p.xchg_tiles;
           const unsigned target = static_cast<unsigned>(nM) * (static_cast<unsigned>(tile_i / p.xchg_tiles) * p.H + t + 1);
-          unsigned seen = 0, spins = 0;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.flags + xi) : "memory");
-            if (++spins > (1u << 22)) {
-              if (dbgp && lane == 0) { dbgp[8 * warp] = 0xF1A60000u | threadIdx.x; dbgp[8 * warp + 1] = xi; dbgp[8 * warp + 2] = seen; dbgp[8 * warp + 3] = target; __threadfence_system(); }
-              asm volatile("trap;");
+          // one lane polls with relaxed loads and a short sleep in between (an acquire load per iteration costs an L1
+          // invalidate, CCTL.IVALL, each time: 22 M of them per launch in the first version); one acquire at the end
+          if (lane == 0) {
+            unsigned seen = 0, spins = 0;
+            for (;;) {
+              asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.flags + xi) : "memory");
+              if (seen >= target) break;
+              __nanosleep(100);
+              if (++spins > (1u << 22)) {
+                if (dbgp) { dbgp[8 * warp] = 0xF1A60000u | threadIdx.x; dbgp[8 * warp + 1] = xi; dbgp[8 * warp + 2] = seen; dbgp[8 * warp + 3] = target; __threadfence_system(); }
+                asm volatile("trap;");
+              }
             }
-          } while (seen < target);
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.flags + xi) : "memory");
+          }
+          __syncwarp();
           tr.rec(0x41u);
           const float* base = p.xchg + ((static_cast<size_t>(xi) * 2 + (t & 1)) * nM) * (DS_T * PIPE_ROWS) + static_cast<size_t>(row_in_tile) * DS_T;
           // members summed in member order (identical on every CTA of the tile), 8 columns (2 x 16 B per member) at a time
@@ -613,7 +656,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
           fence_after_sync();
         } else {
           const int b = (n_mt == 1) ? b_single : (j & 1);
-          mbar_wait(bar_dout + 8 * b, (b ? oc1 : oc0) & 1u, dbgp, 0x5000000u | j);
+          mbar_wait_sleep(bar_dout + 8 * b, (b ? oc1 : oc0) & 1u, dbgp, 0x5000000u | j);
           if (b) ++oc1; else ++oc0;
           fence_after_sync();
           tr.rec(0x41u);
@@ -634,6 +677,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
           }
         }
         tr.rec(0x42u);
+        if (p.traj && valid && mt_member(i) == 0) {   // user reward: dump the visited state (user_reward.cu)
+          float* tp = p.traj + (static_cast<size_t>(row) * p.H + t) * p.dS;
+#pragma unroll
+          for (int k = 0; k < DS_T; ++k) if (k < p.dS) tp[k] = s2[k];
+        }
         float r_t = 0.0f;
         if (p.reward_id == BBMPC_REWARD_HALFCHEETAH) {
           if constexpr (DS_T >= 18) {
@@ -707,7 +755,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
         const int n_a_chunks = cv[8 * l + 3];
         const float* tail_tab = reinterpret_cast<const float*>(smem + lay.conv + MAX_LAYERS * 32) + 64 * l;
         const uint32_t taddr = tmem_base + lane_off + (b ? p.col_d1 : p.col_d0);
-        mbar_wait(bar_dfull + 8 * b, (b ? hc1 : hc0) & 1u, dbgp, 0x4000000u | (j << 8) | l);
+        mbar_wait_sleep(bar_dfull + 8 * b, (b ? hc1 : hc0) & 1u, dbgp, 0x4000000u | (j << 8) | l);
         if (b) ++hc1; else ++hc0;
         fence_after_sync();
         tr.rec(0x20u | (l << 8) | (b << 12));
@@ -810,6 +858,7 @@ bool pipe_supported(const bbmpc_ctx* ctx, int passes, PipeParams* out) {
   const size_t budget = 227 * 1024;
   // ring sizes: at least 3 weight stages and one layer + 1 unit of activations; spare shared memory goes to the weights
   int a_units = max_units + 1;
+  if (const char* x = getenv("BBMPC_PIPE_AUNITS")) { const int v = atoi(x); if (v >= max_units && v <= PIPE_MAX_UNITS) a_units = v; }   // A/B: ring slack vs weight stages
   if (a_units > PIPE_MAX_UNITS) return false;
   int n_w = PIPE_MAX_WSTAGES;
   while (n_w > 2 && pipe_layout(p.stage_bytes, n_w, a_units, p.a_chunk_bytes, p.n_table, nL).total > budget) --n_w;
@@ -827,7 +876,7 @@ int launch_rollout_pipe(bbmpc_ctx* ctx, const float* states, const float* action
   if (!pipe_supported(ctx, passes, &p)) return -100;
   p.mlp = m.mlp; p.norm = m.norm; p.reward_id = ctx->reward_id; p.dS = m.dS; p.dU = m.dU;
   p.states = states; p.actions = actions; p.returns = returns; p.penalty = penalty;
-  p.rows = rows; p.A = A; p.H = H; p.passes = passes;
+  p.rows = rows; p.A = A; p.H = H; p.passes = passes; p.traj = ctx->traj_cur;
   p.n_tiles = (rows + PIPE_ROWS - 1) / PIPE_ROWS;
   p.jobs = m.mlp.solo_jobs; p.table = m.mlp.solo_table;
   if (const char* x = getenv("BBMPC_TC_X")) p.xflags = atoi(x);

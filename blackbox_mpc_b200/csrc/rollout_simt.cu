@@ -26,6 +26,7 @@ struct SimtParams {
   // rollout
   const float* states; const float* actions; float* returns; const float* penalty;
   int rows, A, H;
+  float* traj;   // user reward: visited states [rows][H][dS] (else nullptr)
   // single step
   StepIO io;
 };
@@ -170,6 +171,8 @@ __global__ void __launch_bounds__(TR* NG) rollout_simt_kernel(const SimtParams p
     dynamics_raw<DYN>(p, sm, lane, g);
     build_output(p, sm, lane, g, norm_on);
     __syncthreads();
+    if (p.traj && valid)
+      for (int i = g; i < p.dS; i += NG) p.traj[(static_cast<size_t>(row) * p.H + t) * p.dS + i] = sm.S2[i * TR + lane];
     if (g == 0) ret = __fadd_rn(ret, row_reward(p, sm, lane));
     __syncthreads();
     for (int i = g; i < p.dS; i += NG) sm.S[i * TR + lane] = sm.S2[i * TR + lane];
@@ -338,7 +341,7 @@ int launch_rollout_simt(bbmpc_ctx* ctx, const float* states, const float* action
   SimtParams p{};
   if (int rc = fill_params(ctx, p)) return rc;
   p.states = states; p.actions = actions; p.returns = returns; p.penalty = penalty;
-  p.rows = rows; p.A = A; p.H = H;
+  p.rows = rows; p.A = A; p.H = H; p.traj = ctx->traj_cur;
   const int grid = (rows + TR - 1) / TR;
   if (p.dyn_id == BBMPC_DYN_MLP) {
     const size_t sb = simt_smem_bytes(p.dS, p.dU, p.mlp.max_width);
@@ -352,7 +355,19 @@ int launch_rollout_simt(bbmpc_ctx* ctx, const float* states, const float* action
   return BBMPC_OK;
 }
 
-int launch_step_simt(bbmpc_ctx* ctx, const StepIO& io, cudaStream_t st) {
+int launch_step_simt(bbmpc_ctx* ctx, const StepIO& io_in, cudaStream_t st) {
+  StepIO io = io_in;
+  if (ctx->reward_id == BBMPC_REWARD_USER && (io.mode & 2)) {
+    // user reward (user_reward.cu): predict with the built-in path, then the JIT-compiled row kernel on (s, a, s')
+    const float* s2 = io.s2_in;
+    if (io.mode & 1) {
+      if (!io.s2_out) return fail(ctx, BBMPC_EINVAL, "user reward after predict needs a next-state buffer");
+      StepIO pred = io; pred.mode = 1; pred.reward_out = nullptr;
+      if (int rc = launch_step_simt(ctx, pred, st)) return rc;
+      s2 = io.s2_out;
+    }
+    return launch_user_reward_rows(ctx, io.s, io.a, s2, io.reward_out, io.B, st);
+  }
   SimtParams p{};
   if (int rc = fill_params(ctx, p)) return rc;
   p.io = io;

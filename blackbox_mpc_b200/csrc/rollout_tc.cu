@@ -80,6 +80,7 @@ struct TcParams {
   int xs_bytes;   // > 0: the group's outputs are staged in shared memory by bulk copies (else read from L2 directly)
   uint32_t* dbg;  // host-mapped watchdog record (BBMPC_DEBUG=1), else nullptr
   uint32_t* trace; // BBMPC_TC_TRACE: per-warp (tag, clock) records of CTA 0, step 1
+  float* traj;    // user reward: visited states [rows][H][dS] (else nullptr)
   int xflags;     // BBMPC_TC_X timing experiments (results are garbage): 1 = no weight loads, 2 = identity activations
 };
 
@@ -597,6 +598,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const TcParam
           }
         }
         // all of this thread's TMEM reads of D_out are complete (wait_ld) before the next arrive.
+        if (p.traj && valid && my_member == 0) {   // user reward: dump the visited state (user_reward.cu)
+          float* tp = p.traj + (static_cast<size_t>(row) * p.H + t) * p.dS;
+#pragma unroll
+          for (int i = 0; i < DS_T; ++i) if (i < p.dS) tp[i] = s2[i];
+        }
         float r_t = 0.0f;
         if (p.reward_id == BBMPC_REWARD_HALFCHEETAH) {
           if constexpr (DS_T >= 18) {
@@ -770,7 +776,7 @@ static int launch_rollout_tc_once(bbmpc_ctx* ctx, const float* states, const flo
   TcParams p{};
   p.mlp = m.mlp; p.norm = m.norm; p.reward_id = ctx->reward_id; p.dS = m.dS; p.dU = m.dU;
   p.states = states; p.actions = actions; p.returns = returns; p.penalty = penalty;
-  p.rows = rows; p.A = A; p.H = H; p.passes = passes;
+  p.rows = rows; p.A = A; p.H = H; p.passes = passes; p.traj = ctx->traj_cur;
   p.n_tiles = (rows + TILE_ROWS - 1) / TILE_ROWS;
   const int stage = m.mlp.stage_bytes;
   int buf_w = 0;

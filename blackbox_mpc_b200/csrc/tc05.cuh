@@ -44,6 +44,34 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// try_wait with an explicit suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the
+// hint elapses.  Without a hint the default limit is short and a waiting warp burns issue slots in its retry loop
+// (ncu, profiles/r2*: tens of millions of TRYWAIT iterations per launch from warps that wait for whole layers).
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok;
+}
+// Long waits (a whole layer or step): sleeps up to ~20 us per attempt; traps after ~1 s.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, volatile uint32_t* dbg = nullptr, uint32_t tag = 0) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (++spins > (1u << 16)) {
+      if (dbg && (threadIdx.x & 31) == 0) {
+        const uint32_t slot = 8u * (threadIdx.x >> 5) + 256u * (blockIdx.x & 1);
+        dbg[slot + 0] = 0xDEAD0000u | threadIdx.x; dbg[slot + 1] = bar; dbg[slot + 2] = parity; dbg[slot + 3] = tag;
+        __threadfence_system();
+      }
+      asm volatile("trap;");
+    }
+  }
+}
 #ifndef TC05_WATCHDOG_SPINS
 #define TC05_WATCHDOG_SPINS (1u << 24)
 #endif

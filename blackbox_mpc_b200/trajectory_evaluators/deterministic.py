@@ -15,11 +15,13 @@ from .evaluator_base import EvaluatorBase
 
 def reward_id_of(reward_function) -> int:
     rid = getattr(reward_function, "bbmpc_reward_id", None)
+    if rid is None and isinstance(getattr(reward_function, "cuda_source", None), str):
+        rid = _lib.REWARD_USER     # any callable that carries its CUDA source (utils/rewards.py)
     if rid is None:
         raise TypeError(
             "reward_function must be a built-in device reward (utils.pendulum.pendulum_reward_function, "
-            "utils.halfcheetah.reward_function, ...): arbitrary Python callables cannot be fused into the "
-            "sm_100a rollout kernel")
+            "utils.halfcheetah.reward_function, ...) or carry CUDA source (utils.rewards.cuda_reward(...), or any callable "
+            "with a `cuda_source` attribute): a plain Python callable cannot run inside the sm_100a rollout kernel")
     return int(rid)
 
 
@@ -31,7 +33,10 @@ class DeterministicTrajectoryEvaluator(EvaluatorBase):
     # -- engine plumbing ----------------------------------------------------------------------
     def engine(self):
         e = self._system_dynamics_handler.ensure_staged()
-        e.check(e.lib.bbmpc_reward_set_builtin(e.handle, self._reward_id))
+        if self._reward_id == _lib.REWARD_USER:   # compiled once per engine and source; a no-op afterwards
+            e.check(e.lib.bbmpc_reward_set_nvrtc(e.handle, self._reward_function.cuda_source.encode()))
+        else:
+            e.check(e.lib.bbmpc_reward_set_builtin(e.handle, self._reward_id))
         return e
 
     def _dev(self, x):

@@ -38,6 +38,7 @@ extern "C" {
                                        -> its `actions` argument receives next_state (reference behaviour) */
 #define BBMPC_REWARD_HALFCHEETAH 2  /* tutorials/mujoco/cost_func.py:5-22 */
 #define BBMPC_REWARD_PENDULUM_GYM 3 /* pendulum reward with the arguments as its docstring intends (s, s', a) */
+#define BBMPC_REWARD_USER 4         /* CUDA source supplied through bbmpc_reward_set_nvrtc */
 
 /* activation ids for bbmpc_model_set_mlp */
 #define BBMPC_ACT_NONE 0
@@ -101,6 +102,12 @@ int bbmpc_model_set_norm(bbmpc_ctx* ctx, int dS, int dU, const float* mean_s, co
 /* Analytical true model (true_model=True: raw concat in, s' = s + f(x) out). */
 int bbmpc_model_set_builtin(bbmpc_ctx* ctx, int dyn_id, int dS, int dU);
 int bbmpc_reward_set_builtin(bbmpc_ctx* ctx, int reward_id);
+/* User-supplied reward_function (policies/mpc_policy.py:42-44; e.g. tutorials/mujoco/cost_func.py:5-22) as CUDA source
+ * defining  __device__ float reward(const float* s, const float* a, const float* s2)  over dS / dU / dS floats
+ * (BBMPC_DS and BBMPC_DU are predefined macros).  Compiled once per context with NVRTC (sm_100a, --fmad=false: plain
+ * IEEE fp32 operations); every rollout then sums it over the visited states, every bbmpc_reward call applies it row-wise.
+ * Needs a model (dS, dU) to be set first.  Compilation errors return BBMPC_EINVAL with the NVRTC log as error text. */
+int bbmpc_reward_set_nvrtc(bbmpc_ctx* ctx, const char* cuda_source);
 
 /* ---- evaluator: trajectory_evaluators/deterministic.py ----------------------------------- */
 /* __call__ (:26-77): returns[P,A] = sum_t reward(s_t, a_t, s_{t+1}), NaN -> -1e6.

@@ -61,7 +61,8 @@ OPT_CASES = {
     "opt_pi2_c2": ("C2", "PI2", 64, 2, 12, "draws.std.pi2.samples", dict(max_iterations=3)),
     "opt_rs_c1": ("C1", "RandomSearch", 64, 2, 12, "draws.std.rs.samples", dict()),
     "opt_spsa_c2": ("C2", "SPSA", 32, 1, 12, "draws.spsa.delta", dict(max_iterations=3)),
-    "opt_cmaes_c2": ("C2", "CMA-ES", 48, 1, 8, "draws.cmaes.z", dict(max_iterations=3, num_elite=12)),
+    # CMA-ES is covered by tests/test_gpu_cmaes.py with injected z AND eigenvectors: the basis of a (nearly) degenerate
+    # covariance is not unique (fp32 syevd here, fp64 SVD in the fixture), so injected z alone cannot reproduce the run.
 }
 
 

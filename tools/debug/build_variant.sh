@@ -3,7 +3,7 @@
 set -e
 SUF=$1; shift
 D=blackbox_mpc_b200/csrc; O=/tmp/bbmpc_var_$SUF; mkdir -p $O
-for f in context rollout_simt rollout_tc rollout_pipe optimizers cmaes; do
+for f in context rollout_simt rollout_tc rollout_pipe optimizers cmaes user_reward; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr "$@" -I include -c $D/$f.cu -o $O/$f.o &
 done
 wait
