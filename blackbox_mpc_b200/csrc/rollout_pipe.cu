@@ -45,6 +45,9 @@
 namespace bbmpc {
 using namespace tc05;
 
+#ifndef PIPE_ISSUE_VARIANT
+#define PIPE_ISSUE_VARIANT 0   // how the MMA issuer emits a ring unit (A/B builds, tools/debug/build_variant.sh)
+#endif
 constexpr int PIPE_WARPS = 20;
 constexpr int PIPE_THREADS = 32 * PIPE_WARPS;
 constexpr int PIPE_MAX_MT = 3;          // member-tiles per CTA and round
@@ -71,11 +74,12 @@ struct PipeParams {
   float* traj;                       // user reward: visited states [rows][H][dS] (else nullptr)
   float* park;                       // integrators' parked states: [grid][PIPE_MAX_MT][DS_T/4 + 1][128] float4
   uint32_t* trace; int xflags;
+  int stagger;                       // cycles by which the odd-chunk conversion warps start late (de-phases compute / store)
   uint32_t* dbg;                     // host-mapped watchdog record (BBMPC_DEBUG=1), else nullptr
 };
 
 struct PipeSmem { uint32_t wring, aring, table, jobs, bars, tmem_slot, stats, conv, total; };
-constexpr int PIPE_NUM_BARS = 2 * PIPE_MAX_WSTAGES + 2 * PIPE_MAX_UNITS + 6 + PIPE_MAX_MT;
+constexpr int PIPE_NUM_BARS = 2 * PIPE_MAX_WSTAGES + 2 * PIPE_MAX_UNITS + 8 + PIPE_MAX_MT;
 __host__ __device__ inline PipeSmem pipe_layout(int stage_bytes, int n_wstages, int a_units, int a_chunk_bytes, int n_table, int n_layers) {
   PipeSmem L;
   uint32_t off = 0;
@@ -170,10 +174,17 @@ __device__ __forceinline__ void pconv_tail(const uint32_t (&r)[16], bool has_dat
 template <int ACT, bool TR>
 __device__ __forceinline__ void pipe_convert(uint32_t taddr, int Npad, int N, int n_a_chunks, int sub, int passes,
                                             uint32_t aring, uint32_t chunk_bytes, uint32_t a_units, uint32_t pu, uint32_t wrap,
-                                            uint32_t bar_afull, uint32_t bar_afree, uint32_t bar_drained, int row, int lane,
-                                            const float* tail_tab, volatile uint32_t* dbgp, PTracer<TR>& tr) {
+                                            uint32_t bar_afull, uint32_t bar_afree, uint32_t bar_drained, uint32_t bar_adone, int row, int lane,
+                                            const float* tail_tab, int stagger, volatile uint32_t* dbgp, PTracer<TR>& tr) {
+  // bar_adone != 0 (two jobs in flight): the MMA issuer waits once for the whole operand instead of per ring unit
   const int n_full = N >> 4;        // chunks whose 16 columns are all real features
   const int n_data = Npad >> 4;     // chunks that carry accumulator data at all
+  if (sub && stagger > 0) {
+    // The two warps of a quarter share one scheduler and one MUFU pipe: started together they compute together and
+    // store together; half a step apart one converts while the other waits for its stores / ring units.
+    const long long t0 = clock64();
+    while (clock64() - t0 < stagger) {}
+  }
   const uint32_t unit_bytes = 2 * chunk_bytes;
   uint32_t slot = aring + pu * unit_bytes + static_cast<uint32_t>(sub) * chunk_bytes + static_cast<uint32_t>(row) * 16;
   uint32_t bf = bar_afull + 8 * pu;
@@ -202,20 +213,28 @@ __device__ __forceinline__ void pipe_convert(uint32_t taddr, int Npad, int N, in
     uint32_t ra[16], rb[16];
     tmem_ld16(taddr + 16 * c, ra);
     tmem_ld16(taddr + 16 * (c + 2), rb);
+    // probe the two ring units now (non-blocking); the answers are needed only after the conversion
+    uint32_t ok0 = 1, ok1 = 1;
+    {
+      uint32_t bf1 = bf + 8, wrap1 = wrap;
+      if (bf1 == bf_end) { bf1 = bar_afull; ++wrap1; }
+      if (wrap > 0) ok0 = mbar_test_wait(bf + free_off, (wrap - 1) & 1u);
+      if (wrap1 > 0) ok1 = mbar_test_wait(bf1 + free_off, (wrap1 - 1) & 1u);
+    }
     wait_ld();
     if (c + 4 >= n_data) drained();
     uint32_t hia[8], loa[8], hib[8], lob[8];
     pconv_full<ACT>(ra, hia, loa);
     pconv_full<ACT>(rb, hib, lob);
     tr.rec(0x200u | c);
-    if (wrap > 0) mbar_wait_sleep(bf + free_off, (wrap - 1) & 1u, dbgp, 0x8000000u | (c << 8));
+    if (!ok0) mbar_wait_sleep(bf + free_off, (wrap - 1) & 1u, dbgp, 0x8000000u | (c << 8));
     const uint32_t slot0 = slot, bf0 = bf;
     store(hia, loa, slot0);
     advance();
-    if (wrap > 0) mbar_wait_sleep(bf + free_off, (wrap - 1) & 1u, dbgp, 0x8100000u | (c << 8));
+    if (!ok1) mbar_wait_sleep(bf + free_off, (wrap - 1) & 1u, dbgp, 0x8100000u | (c << 8));
     store(hib, lob, slot);
     fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
-    mbar_arrive(bf0);
+    mbar_arrive(bf0);   // (per-unit arrivals in every mode: the barrier phases must stay in step with the ring across rounds)
     if (((c + 2) ^ 1) < n_a_chunks) mbar_arrive(bf); else mbar_arrive_n(bf, 2);
     advance();
     tr.rec(0x300u | c);
@@ -237,6 +256,10 @@ __device__ __forceinline__ void pipe_convert(uint32_t taddr, int Npad, int N, in
     tr.rec(0x300u | c);
   }
   if (sub >= n_data) drained();   // no chunk of this warp carried accumulator data
+  if (bar_adone) {                // every lane's stores are fenced (above) before its warp's arrival
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_adone);
+  }
 }
 
 template <int DS_T, int DU_T, bool TR, int ACT_T>
@@ -256,7 +279,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
   const uint32_t bar_dfull = bar_afree + PIPE_MAX_UNITS * 8;       // MMA -> conversion: hidden accumulator in D[b] complete
   const uint32_t bar_dout = bar_dfull + 16;                        // MMA -> publishers / integrators: output accumulator in D[b]
   const uint32_t bar_drained = bar_dout + 16;                      // readers -> MMA: D[b] has been read (8 arrivals)
-  const uint32_t bar_xfull = bar_drained + 16;                     // integrators -> MMA: X region i written (4 arrivals)
+  const uint32_t bar_adone = bar_drained + 16;                     // conversion -> MMA (two jobs in flight): the whole A operand of slot b is in the ring (8 arrivals)
+  const uint32_t bar_xfull = bar_adone + 16;                       // integrators -> MMA: X region i written (4 arrivals)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + lay.tmem_slot);
   float* st_mean_t = reinterpret_cast<float*>(smem + lay.stats);
   float* st_den_t = st_mean_t + MAX_DS;
@@ -291,6 +315,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
     for (int s = 0; s < p.n_wstages; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
     for (int u = 0; u < p.a_units; ++u) { mbar_init(bar_afull + 8 * u, 256); mbar_init(bar_afree + 8 * u, 1); }   // 2 chunks x 4 quarters x 32 lanes
     for (int b = 0; b < 2; ++b) { mbar_init(bar_dfull + 8 * b, 1); mbar_init(bar_dout + 8 * b, 1); mbar_init(bar_drained + 8 * b, 8); }
+    for (int b = 0; b < 2; ++b) mbar_init(bar_adone + 8 * b, 8);
     for (int i = 0; i < PIPE_MAX_MT; ++i) mbar_init(bar_xfull + 8 * i, 4);
     fence_mbar_init();
     int* cv = reinterpret_cast<int*>(smem + lay.conv);
@@ -364,6 +389,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
       uint32_t useq = 0;                    // ring units allocated so far (mirrors the conversion warps)
       uint32_t dw0 = 0, dw1 = 0;            // stages issued into D[0] / D[1]
       uint32_t xc0 = 0, xc1 = 0, xc2 = 0;   // layer-0 inputs consumed per X region (barrier phases persist across rounds)
+      uint32_t ad0 = 0, ad1 = 0;            // whole-operand completions consumed per slot (two jobs in flight)
       const uint32_t wring16 = (smem_base + lay.wring) >> 4, stage16 = static_cast<uint32_t>(p.stage_bytes) >> 4;
       const uint32_t aring16 = (smem_base + lay.aring) >> 4, achunk16 = static_cast<uint32_t>(p.a_chunk_bytes) >> 4;
       constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);          // SBO = 128 B, descriptor version 1, no swizzle
@@ -400,17 +426,33 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
           uint32_t wrap = ub / p.a_units, pu = ub - wrap * p.a_units;
           fence_after_sync();
           tr.rec(0x1000u | (l << 8) | (b << 4));
-          uint32_t acc = 0, u = 0, pre_ok = 0;
+          uint32_t acc = 0, u = 0;
           const uint32_t n_units = (job.nchunks + 1u) >> 1;
           const uint32_t xcol = tmem_base + p.col_x + i * p.x_w;
+          // BBMPC_TC_X & 32: wait for the whole converted operand (bar_adone) instead of per ring unit.  Measured slower
+          // (1.356 vs 1.237 ms per C4 rollout): the stage then starts ~2k cycles later, after the last conversion step.
+          const bool whole = (p.xflags & 32) && !seq.single && l > 0;
+          if (whole) {
+            mbar_wait(bar_adone + 8 * b, (b ? ad1 : ad0) & 1u, dbgp, 0x1200000u | (j << 8) | l);
+            if (b) ++ad1; else ++ad0;
+            fence_after_sync();
+          }
+          // Readiness of the CURRENT unit's weight stage / ring unit, learnt from the probe issued with the previous unit
+          // (ok_w only matters at the first unit of a group, ok_a at every unit of a layer >= 1 in single mode).
+          uint32_t ok_w = 0, ok_a = 0;
           for (uint32_t g = 0; g < job.ngroups; ++g) {
             const uint32_t n = (job.gsz >> (4 * g)) & 15u;
-            mbar_wait(bar_wfull + 8 * stage, phase, dbgp, 0x3000000u | (l << 8) | g);
+            tr.rec(0x4000u | g);
+            if (!ok_w) mbar_wait(bar_wfull + 8 * stage, phase, dbgp, 0x3000000u | (l << 8) | g);
+            tr.rec(0x4100u | g);
             const uint32_t sbase = wring16 + stage * stage16;
+            uint32_t nstage = stage + 1, nphase = phase;            // next group's weight stage (probed with this group's last unit)
+            if (nstage == static_cast<uint32_t>(p.n_wstages)) { nstage = 0; nphase ^= 1; }
             for (uint32_t k = 0; k < n; ++k, ++u) {
               const bool two = 2 * u + 1 < job.nchunks;
               const uint32_t blo = job.desc_lo_base | ((sbase + 2 * k * job.chunk16) & 0x3FFFu);
               const uint64_t b0 = (static_cast<uint64_t>(DESC_HI) << 32) | blo;
+              const bool last_of_group = (k + 1 == n);
               if (l == 0) {
                 fence_after_sync();
                 if (elect_one()) {
@@ -422,19 +464,35 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
                     mma_ts(d, a0 + 16, b1, job.idesc, 1u);
                     if (three) { mma_ts(d, a0 + 24, b1, job.idesc, 1u); mma_ts(d, a0 + 16, b1 + job.lo_off16, job.idesc, 1u); }
                   }
+                  if (last_of_group) mma_commit(bar_wempty + 8 * stage);
                 }
                 __syncwarp();
+                ok_w = 0;
               } else {
-                if (!pre_ok) mbar_wait_poll(bar_afull + 8 * pu, wrap & 1u, dbgp, 0x2000000u | (j << 12) | (l << 8) | u);
-                {  // probe the next unit before this unit's MMAs are issued (hides the probe latency)
-                  uint32_t pn = pu + 1, wn = wrap;
-                  if (pn == static_cast<uint32_t>(p.a_units)) { pn = 0; ++wn; }
-                  pre_ok = (u + 1 < n_units) ? mbar_test_wait(bar_afull + 8 * pn, wn & 1u) : 0u;
-                }
+                if (!whole && !ok_a) mbar_wait_poll(bar_afull + 8 * pu, wrap & 1u, dbgp, 0x2000000u | (j << 12) | (l << 8) | u);
                 fence_after_sync();
+                tr.rec(0x4200u | u);
+                uint32_t pn = pu + 1, wn = wrap;
+                if (pn == static_cast<uint32_t>(p.a_units)) { pn = 0; ++wn; }
+                const uint32_t alo = a_desc_lo_base | ((aring16 + 2 * pu * achunk16) & 0x3FFFu);
+                const uint64_t a0 = (static_cast<uint64_t>(DESC_HI) << 32) | alo;
+#if PIPE_ISSUE_VARIANT == 0
+                // one asm block: probes of the next group's weight stage and (single mode) the next ring unit first, the
+                // unit's MMAs and commits by one elected lane, the probe results last (their latency overlaps the issue)
+                uint32_t pw = 0, pa = 0;
+                mma_unit_ss_probe(d, a0, b0, a_lo_off16, job.lo_off16, achunk16, job.chunk16, job.idesc, acc, three ? 1u : 0u, two ? 1u : 0u,
+                                  bar_afree + 8 * pu, last_of_group ? bar_wempty + 8 * stage : 0u,
+                                  bar_wfull + 8 * nstage, nphase, bar_afull + 8 * pn, wn & 1u, pw, pa);
+                ok_w = (last_of_group && g + 1 < job.ngroups) ? pw : 0u;
+                ok_a = (!whole && u + 1 < n_units) ? pa : 0u;
+#else
+                // A/B: C++ elected block (PIPE_ISSUE_VARIANT 1: probes issued before it, 2: no probes)
+                uint32_t pw = 0, pa = 0;
+                if (PIPE_ISSUE_VARIANT == 1) {
+                  pw = (last_of_group && g + 1 < job.ngroups) ? mbar_test_wait(bar_wfull + 8 * nstage, nphase) : 0u;
+                  pa = (!whole && u + 1 < n_units) ? mbar_test_wait(bar_afull + 8 * pn, wn & 1u) : 0u;
+                }
                 if (elect_one()) {
-                  const uint32_t alo = a_desc_lo_base | ((aring16 + 2 * pu * achunk16) & 0x3FFFu);
-                  const uint64_t a0 = (static_cast<uint64_t>(DESC_HI) << 32) | alo;
                   mma_ss(d, a0, b0, job.idesc, acc);
                   if (three) { mma_ss(d, a0 + a_lo_off16, b0, job.idesc, 1u); mma_ss(d, a0, b0 + job.lo_off16, job.idesc, 1u); }
                   if (two) {
@@ -442,16 +500,17 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
                     mma_ss(d, a1, b1, job.idesc, 1u);
                     if (three) { mma_ss(d, a1 + a_lo_off16, b1, job.idesc, 1u); mma_ss(d, a1, b1 + job.lo_off16, job.idesc, 1u); }
                   }
-                  mma_commit(bar_afree + 8 * pu);   // the unit may be refilled when these MMAs retire
+                  mma_commit(bar_afree + 8 * pu);
+                  if (last_of_group) mma_commit(bar_wempty + 8 * stage);
                 }
                 __syncwarp();
-                if (++pu == static_cast<uint32_t>(p.a_units)) { pu = 0; ++wrap; }
+                ok_w = pw; ok_a = pa;
+#endif
+                pu = pn; wrap = wn;
               }
               acc = 1u;
             }
-            if (elect_one()) mma_commit(bar_wempty + 8 * stage);
-            __syncwarp();
-            if (++stage == static_cast<uint32_t>(p.n_wstages)) { stage = 0; phase ^= 1; }
+            stage = nstage; phase = nphase;
           }
           if (elect_one()) mma_commit((l + 1 < nL ? bar_dfull : bar_dout) + 8 * b);
           __syncwarp();
@@ -761,7 +820,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
         tr.rec(0x20u | (l << 8) | (b << 12));
         const uint32_t aring = smem_base + lay.aring;
 #define PIPE_CONV(ACT) pipe_convert<ACT, TR>(taddr, Npad, N, n_a_chunks, sub, p.passes, aring, p.a_chunk_bytes, p.a_units, pu, wrap, \
-                                            bar_afull, bar_afree, bar_drained + 8 * b, row_in_tile, lane, tail_tab, dbgp, tr)
+                                            bar_afull, bar_afree, bar_drained + 8 * b, (seq.single || !(p.xflags & 32)) ? 0u : bar_adone + 8 * b, row_in_tile, lane, tail_tab, p.stagger, dbgp, tr)
         if (ACT_T >= 0) {
           PIPE_CONV((ACT_T >= 0 ? ACT_T : 0));
         } else {
@@ -880,6 +939,8 @@ int launch_rollout_pipe(bbmpc_ctx* ctx, const float* states, const float* action
   p.n_tiles = (rows + PIPE_ROWS - 1) / PIPE_ROWS;
   p.jobs = m.mlp.solo_jobs; p.table = m.mlp.solo_table;
   if (const char* x = getenv("BBMPC_TC_X")) p.xflags = atoi(x);
+  p.stagger = 700;
+  if (const char* x = getenv("BBMPC_PIPE_STAGGER")) p.stagger = atoi(x);
   if (const char* x = getenv("BBMPC_PIPE_MT")) { const int v = atoi(x); if (v >= 1 && v < p.max_mt) p.max_mt = v; }
   if (getenv("BBMPC_TC_TRACE")) {
     static uint32_t* tbuf = nullptr;
@@ -895,6 +956,14 @@ int launch_rollout_pipe(bbmpc_ctx* ctx, const float* states, const float* action
   }
   const int nM = m.mlp.n_members;
   const long long ids = static_cast<long long>(p.n_tiles) * nM;
+  // Launches that give every CTA at most one member-tile have nothing to interleave; there the one-tile-per-CTA kernel
+  // wins (its A operand stays in TMEM: an SS-mode MMA also fetches A from shared memory, (128 + N) / N times the operand
+  // bytes per instruction at the same 64 B/clk — measured 0.59 vs 0.46 ms for a 1 250-row C4 shard).  BBMPC_TC_PIPE=1 forces
+  // the pipelined kernel for every shape (tests, A/B).
+  {
+    const char* force = getenv("BBMPC_TC_PIPE");
+    if (ids <= ctx->sm_count && !(force && force[0] == '1')) return -100;
+  }
   int grid = ids < ctx->sm_count ? static_cast<int>(ids) : ctx->sm_count;
   if (nM > ctx->sm_count) return -100;
   // rounds are tile-aligned: at most max_mt member-tiles per CTA and round

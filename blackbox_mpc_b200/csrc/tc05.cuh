@@ -177,6 +177,58 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One ring UNIT of an SS contraction (two K-chunks, the second optional; bf16x3 = three MMAs per chunk, else one),
+// issued by one elected lane of a CONVERGED warp, followed by up to two commits, with two non-blocking mbarrier
+// probes issued FIRST and read back LAST.  A satisfied try_wait / test_wait costs ~150-200 cycles of latency in the
+// issuing warp's in-order instruction stream; inside one asm block the probes' latency overlaps the MMA issue, and the
+// caller only blocks on a barrier whose probe failed (trace: 1300 -> ~500 cycles per unit in the issuer, profiles/r2*).
+//   a0 / b0: descriptors of chunk 0 (hi image); *_lo: offset of the bf16-lo image; *_chunk: offset of chunk 1 (all in
+//   descriptor units of 16 bytes, added to the 64-bit descriptor).  commit1 == 0: no second commit.
+// (A variant of this block specialised at compile time on three / two / commit1, every instruction guarded by the elect
+// predicate only, measured SLOWER: 1.352 vs 1.237 ms per C4 rollout — eight copies of the block in the issuer's loop.)
+__device__ __forceinline__ void mma_unit_ss_probe(uint32_t d_tmem, uint64_t a0, uint64_t b0, uint32_t a_lo, uint32_t b_lo,
+                                                  uint32_t a_chunk, uint32_t b_chunk, uint32_t idesc, uint32_t acc,
+                                                  uint32_t three, uint32_t two, uint32_t commit0, uint32_t commit1,
+                                                  uint32_t probe0, uint32_t parity0, uint32_t probe1, uint32_t parity1,
+                                                  uint32_t& ok0, uint32_t& ok1) {
+  // operands: %0 ok0, %1 ok1 | %2 d, %3 a0, %4 b0, %5 a_lo, %6 b_lo, %7 a_chunk, %8 b_chunk, %9 idesc, %10 acc, %11 three,
+  //           %12 two, %13 commit0, %14 commit1, %15 probe0, %16 parity0, %17 probe1, %18 parity1
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q0, q1, pe, pacc, p3, p2, p23, pc1, pt;\n\t"
+      ".reg .b64 al, bl, a1, b1, a1l, b1l, t;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q0, [%15], %16;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q1, [%17], %18;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pacc, %10, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "setp.ne.b32 p3, %11, 0;\n\t"
+      "and.pred p3, p3, pe;\n\t"
+      "setp.ne.b32 p2, %12, 0;\n\t"
+      "and.pred p2, p2, pe;\n\t"
+      "and.pred p23, p2, p3;\n\t"
+      "setp.ne.b32 pc1, %14, 0;\n\t"
+      "and.pred pc1, pc1, pe;\n\t"
+      "cvt.u64.u32 t, %5;\n\t add.u64 al, %3, t;\n\t"
+      "cvt.u64.u32 t, %6;\n\t add.u64 bl, %4, t;\n\t"
+      "cvt.u64.u32 t, %7;\n\t add.u64 a1, %3, t;\n\t add.u64 a1l, al, t;\n\t"
+      "cvt.u64.u32 t, %8;\n\t add.u64 b1, %4, t;\n\t add.u64 b1l, bl, t;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], %3, %4, %9, pacc;\n\t"
+      "@p3 tcgen05.mma.cta_group::1.kind::f16 [%2], al, %4, %9, pt;\n\t"
+      "@p3 tcgen05.mma.cta_group::1.kind::f16 [%2], %3, bl, %9, pt;\n\t"
+      "@p2 tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1, %9, pt;\n\t"
+      "@p23 tcgen05.mma.cta_group::1.kind::f16 [%2], a1l, b1, %9, pt;\n\t"
+      "@p23 tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1l, %9, pt;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%13];\n\t"
+      "@pc1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%14];\n\t"
+      "selp.u32 %0, 1, 0, q0;\n\t"
+      "selp.u32 %1, 1, 0, q1;\n\t"
+      "}"
+      : "=r"(ok0), "=r"(ok1)
+      : "r"(d_tmem), "l"(a0), "l"(b0), "r"(a_lo), "r"(b_lo), "r"(a_chunk), "r"(b_chunk), "r"(idesc), "r"(acc), "r"(three),
+        "r"(two), "r"(commit0), "r"(commit1), "r"(probe0), "r"(parity0), "r"(probe1), "r"(parity1)
+      : "memory");
+}
 // All previously issued MMAs of this thread arrive (count 1) on `bar` when they complete.
 // Implies tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
