@@ -257,9 +257,14 @@ def run_ours(args):
         return t.item(), engine.launch_count - launches0, kern
 
     with ClockSampler(local_rank) as clocks:
-        total_ms, launches, (kern_ms, kern_n) = timed(device_step, args.steps, args.warmup, profile=True)
+        # one act() = one CUDA-graph launch (bbmpc_opt_call replays its captured kernels; sharded runs stay eager)
+        total_ms, launches, _ = timed(device_step, args.steps, args.warmup)
         # end to end through the public API: host numpy in, host numpy out, every step
         e2e_ms, _, _ = timed(host_step, args.steps, max(3, args.warmup // 2))
+        # rollout-kernel time for the roofline: a separate profiled pass (event pairs around every rollout launch on its
+        # stream; profiling runs the act() eagerly, the kernel itself is the same)
+        prof_steps = min(args.steps, 20)
+        _, _, (kern_ms, kern_n) = timed(device_step, prof_steps, 3, profile=True)
     exchange = "none (1 GPU)"
     ranks_agree = None
     if world > 1:
@@ -297,8 +302,9 @@ def run_ours(args):
                 traffic = None
         roofline = {
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": traffic, "kernel": "rollout_tc_kernel" if eff_prec != "fp32" else "rollout_simt_kernel",
-            "kernel_ms_avg": avg_ms, "kernel_launches": kern_n, "kernel_share_of_step": kern_ms / total_ms,
+            "traffic": traffic, "kernel": engine.last_rollout_kernel,
+            "kernel_ms_avg": avg_ms, "kernel_launches": kern_n, "kernel_launches_per_step": kern_n / prof_steps,
+            "kernel_share_of_step": (kern_ms / prof_steps) / (total_ms / args.steps),
             "algorithmic_flops_per_launch": flops_per_launch, "peak_source": f"{peaks['_source']} bf16_tflops_sustained (dense cuBLAS bf16)",
             "note": ("operands are split into bf16 hi+lo and contracted in 3 tensor-core passes with fp32 accumulation "
                      "(fp32-grade parity with the reference); algorithmic FLOPs are counted once, so the ceiling of frac is 1/3"
@@ -316,6 +322,8 @@ def run_ours(args):
         "e2e": {"value": 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "api": "MPCPolicy.act(numpy obs) -> numpy (action, next_obs, reward)"},
         "gpu_launches": int(launches),
+        "act_launch": ("one CUDA-graph launch per act() (kernels counted inside the graph)" if world == 1 and not os.environ.get("BBMPC_NO_GRAPH")
+                       else "eager kernel launches"),
         "roofline": roofline,
     }
     if not args.no_cpu_baseline and world == 1:

@@ -45,6 +45,7 @@ SIGNATURES = {
     "bbmpc_set_precision": (_I, [_VP, _I]),
     "bbmpc_get_effective_precision": (_I, [_VP]),
     "bbmpc_launch_count": (_U64, [_VP]),
+    "bbmpc_last_rollout_kernel": (C.c_char_p, [_VP]),
     "bbmpc_profile_enable": (_I, [_VP, _I]),
     "bbmpc_profile_read": (_I, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "bbmpc_model_set_mlp": (_I, [_VP, _I, _I, C.POINTER(_I), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_I), _VP]),

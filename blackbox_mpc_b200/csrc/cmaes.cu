@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) cmaes_sample_kernel(const float* __restri
                                                            const float* __restrict__ ub, float* __restrict__ x,
                                                            float* __restrict__ excess_sq, float* __restrict__ z_trace,
                                                            const float* __restrict__ z_inject, int P_local, int p0, int N, int dU, uint64_t seed,
-                                                           uint32_t act_call, uint32_t iter) {
+                                                           const uint32_t* act_ctr, uint32_t iter) {
   __shared__ float zs[CK][CT + 1];
   __shared__ float bs[CK][CT];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) cmaes_sample_kernel(const float* __restri
     {  // z tile: thread -> (row = tid / 4, 4 consecutive k)
       const int r = tid >> 2, kq = (tid & 3) * 4, row = row0 + r;
       Philox4 w{0u, 0u, 0u, 0u};
-      if (row < P_local && k0 + kq < N) w = draw_block(seed, act_call, STREAM_SAMPLES, iter, static_cast<uint32_t>(p0 + row), (k0 + kq) >> 2);
+      if (row < P_local && k0 + kq < N) w = draw_block(seed, *act_ctr, STREAM_SAMPLES, iter, static_cast<uint32_t>(p0 + row), (k0 + kq) >> 2);
       const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -348,7 +348,7 @@ int cmaes_iter_local(bbmpc_opt* o, int iter, float* partial, cudaStream_t st) {
       ++o->inject_iter;
     }
     cmaes_sample_kernel<<<grid, 256, 0, st>>>(o->d_BD, o->d_m, o->d_sigma, o->d_lb, o->d_ub, o->d_samples, o->d_work, z_trace,
-                                              z_inject, o->P_local, o->p0, N, c.dU, ctx->seed, o->act_call, static_cast<uint32_t>(iter));
+                                              z_inject, o->P_local, o->p0, N, c.dU, ctx->seed, o->d_act_ctr, static_cast<uint32_t>(iter));
     BB_LAUNCH_CHECK(ctx);
     const int64_t rows = static_cast<int64_t>(o->P_local) * A;
     launch_penalty(o->d_work, o->d_penalty, rows, o->HU, st); BB_LAUNCH_CHECK(ctx);

@@ -109,6 +109,8 @@ struct bbmpc_ctx {
   int reward_id = 0;
   bbmpc::ModelHost model;
   uint64_t launches = 0;
+  uint64_t epoch = 1;        // bumped whenever model / statistics / reward / precision change: invalidates captured act() graphs
+  std::string last_rollout_kernel;   // name of the kernel the last rollout launched (bench.py's roofline line)
   std::string err;
   // few-row step kernel (optimizer tail): per-member partial outputs + arrival counters
   float* step_scratch = nullptr;

@@ -138,16 +138,18 @@ int rollout_dispatch(bbmpc_ctx* ctx, const float* states, const float* actions, 
   ctx->traj_cur = nullptr;
   if (user_reward && H > 0)
     if (int rc2 = user_reward_traj_buffer(ctx, rows, H, st, &ctx->traj_cur)) return rc2;
-  if (prec == BBMPC_PREC_FP32)
+  if (prec == BBMPC_PREC_FP32) {
     rc = launch_rollout_simt(ctx, states, actions, returns, penalty, rows, A, H, 0, st);
-  else {
+    ctx->last_rollout_kernel = "rollout_simt_kernel";
+  } else {
     // pipelined kernel (two jobs in flight per CTA) when the model fits its TMEM / shared-memory budget;
     // BBMPC_TC_PIPE=0 keeps the one-tile-per-CTA kernel (A/B measurements)
     const int passes = prec == BBMPC_PREC_BF16 ? 1 : 3;
     const char* pipe_env = getenv("BBMPC_TC_PIPE");
     rc = -100;
     if (H > 0 && !(pipe_env && pipe_env[0] == '0')) rc = launch_rollout_pipe(ctx, states, actions, returns, penalty, rows, A, H, passes, st);
-    if (rc == -100) rc = launch_rollout_tc(ctx, states, actions, returns, penalty, rows, A, H, passes, st);
+    ctx->last_rollout_kernel = "rollout_pipe_kernel";
+    if (rc == -100) { rc = launch_rollout_tc(ctx, states, actions, returns, penalty, rows, A, H, passes, st); ctx->last_rollout_kernel = "rollout_tc_kernel"; }
   }
   if (rc == BBMPC_OK && user_reward)
     rc = launch_user_reward_traj(ctx, ctx->traj_cur, states, actions, penalty, returns, rows, A, H, st);
@@ -211,6 +213,7 @@ void bbmpc_ctx_destroy(bbmpc_ctx* ctx) {
 int bbmpc_set_precision(bbmpc_ctx* ctx, int prec) {
   if (!ctx) return BBMPC_EINVAL;
   if (prec < BBMPC_PREC_AUTO || prec > BBMPC_PREC_BF16) return fail(ctx, BBMPC_EINVAL, "unknown precision %d", prec);
+  if (ctx->prec != prec) ctx->epoch++;
   ctx->prec = prec;
   return BBMPC_OK;
 }
@@ -218,6 +221,8 @@ int bbmpc_set_precision(bbmpc_ctx* ctx, int prec) {
 int bbmpc_get_effective_precision(const bbmpc_ctx* ctx) { return ctx ? resolve_precision(ctx) : BBMPC_EINVAL; }
 
 uint64_t bbmpc_launch_count(const bbmpc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+const char* bbmpc_last_rollout_kernel(const bbmpc_ctx* ctx) { return ctx ? ctx->last_rollout_kernel.c_str() : ""; }
 
 int bbmpc_profile_enable(bbmpc_ctx* ctx, int on) {
   if (!ctx) return BBMPC_EINVAL;
@@ -254,6 +259,7 @@ int bbmpc_model_set_mlp(bbmpc_ctx* ctx, int n_members, int n_layers, const int* 
   BB_CUDA(ctx, cudaSetDevice(ctx->device));
   ModelHost& m = ctx->model;
   BB_CUDA(ctx, cudaStreamSynchronize(st));  // nothing in flight may still read the old image
+  ctx->epoch++;
   free_model(m);
   m.dyn_id = BBMPC_DYN_MLP;
   MlpDev& p = m.mlp;
@@ -430,6 +436,7 @@ int bbmpc_model_set_norm(bbmpc_ctx* ctx, int dS, int dU, const float* mean_s, co
   ModelHost& m = ctx->model;
   if (m.set && m.dyn_id == BBMPC_DYN_MLP && (m.dS != dS || m.dU != dU))
     return fail(ctx, BBMPC_EINVAL, "norm dims dS=%d dU=%d differ from the model's dS=%d dU=%d", dS, dU, m.dS, m.dU);
+  ctx->epoch++;
   m.dS = dS; m.dU = dU;
   const int n_null = !mean_s + !std_s + !mean_a + !std_a + !mean_t + !std_t;
   if (n_null == 6) { m.norm = NormDev{}; return BBMPC_OK; }
@@ -454,6 +461,7 @@ int bbmpc_model_set_builtin(bbmpc_ctx* ctx, int dyn_id, int dS, int dU) {
   if (dS != 3 || dU != 1) return fail(ctx, BBMPC_EINVAL, "pendulum model needs dS=3 dU=1 (got %d, %d)", dS, dU);
   BB_CUDA(ctx, cudaSetDevice(ctx->device));
   BB_CUDA(ctx, cudaDeviceSynchronize());
+  ctx->epoch++;
   free_model(ctx->model);
   ctx->model.dyn_id = dyn_id;
   ctx->model.dS = dS; ctx->model.dU = dU;
@@ -467,6 +475,7 @@ int bbmpc_reward_set_builtin(bbmpc_ctx* ctx, int reward_id) {
   if (!ctx) return BBMPC_EINVAL;
   if (reward_id < BBMPC_REWARD_PENDULUM || reward_id > BBMPC_REWARD_PENDULUM_GYM)
     return fail(ctx, BBMPC_EINVAL, "unknown reward id %d", reward_id);
+  if (ctx->reward_id != reward_id) ctx->epoch++;
   ctx->reward_id = reward_id;
   return BBMPC_OK;
 }

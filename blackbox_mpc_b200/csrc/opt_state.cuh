@@ -10,7 +10,9 @@ struct bbmpc_opt {
   int p0 = 0, P_local = 0;        // this rank's slice [p0, p0 + P_local) of the population
   int n_eval = 0;                 // rows of the population axis handed to the evaluator (SPSA: 2*P_local)
   int HU = 0, AHU = 0;            // H*dU, A*H*dU
-  uint32_t act_call = 0;
+  int cem_slices = 1;             // population slices of the last unsharded CEM top-E (their messages sit back to back in d_partial)
+  uint32_t act_call = 0;          // host mirror of *d_act_ctr
+  uint32_t* d_act_ctr = nullptr;  // act() calls completed so far (Philox counter word), bumped by the last kernel of every call
   int time_step = 0;
   bool began = false;
   // device state
@@ -46,6 +48,10 @@ struct bbmpc_opt {
   // injected standard variates (tests: committed golden draws): block k serves the k-th iteration since it was set
   const float* inject = nullptr; int64_t inject_floats = 0; int64_t inject_iter = 0;
   float* h_pinned = nullptr;
+  // captured act(): the kernels of bbmpc_opt_call on the handle's own buffers, replayed with cudaGraphLaunch
+  cudaGraphExec_t graph_exec = nullptr; uint64_t graph_epoch = 0; int graph_noise = -1; int graph_warm = 0;
+  cudaStream_t graph_stream = nullptr;   // capture stream (the caller's stream may be the legacy default stream)
+  uint64_t graph_launches = 0;   // kernels inside the captured graph (bbmpc_launch_count stays a kernel count)
   std::vector<void*> owned;
 };
 
@@ -60,5 +66,6 @@ int cmaes_iter_local(bbmpc_opt* o, int iter, float* partial, cudaStream_t st);
 int cmaes_iter_merge(bbmpc_opt* o, int iter, const float* partials, int world, cudaStream_t st);
 // shared kernels implemented in optimizers.cu
 void launch_penalty(const float* excess_sq, float* penalty, int64_t rows, int HU, cudaStream_t st);
-void launch_topk_partial(const float* returns, const float* samples, float* partial, int P_local, int p0, int A, int HU, int E, cudaStream_t st);
+void launch_topk_partial(const float* returns, const float* samples, float* partial, int P_local, int p0, int A, int HU, int E, cudaStream_t st,
+                         int n_slices = 1, int64_t slice_stride = 0);
 }  // namespace bbmpc

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "device_fns.cuh"
 #include "refit.cuh"
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges show up in Nsight tools, no-ops otherwise
 #include "opt_state.cuh"
 
 using namespace bbmpc;
@@ -30,6 +31,11 @@ int dalloc(bbmpc_opt* o, T** p, size_t n) {
   return BBMPC_OK;
 }
 
+struct NvtxRange {   // sample / rollout / refit phases of an act()
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 // ============================================================================ kernels
 // ---- fills / small vector ops
 __global__ void fill_midpoint_kernel(float* out, const float* lb, const float* ub, int n, int dU) {
@@ -45,6 +51,7 @@ __global__ void fill_kernel(float* out, float v, int64_t n) {
   if (i < n) out[i] = v;
 }
 // out[a,h,:] = in[a,min(h+1,H-1),:]   (pi2.py:92-93, spsa.py:114-115)
+__global__ void act_ctr_bump_kernel(uint32_t* ctr) { *ctr += 1u; }   // last kernel of an act(): next call draws from fresh Philox counters
 __global__ void shift_left_kernel(const float* in, float* out, int A, int H, int dU) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A * H * dU) return;
@@ -54,13 +61,13 @@ __global__ void shift_left_kernel(const float* in, float* out, int A, int H, int
 }
 // action[a,:] = sol[a,0,:]  (+ exploration noise and clip, optimizer_base.py:82-90)
 __global__ void first_action_kernel(const float* sol, float* action, const float* lb, const float* ub, int A,
-                                    int H, int dU, int sol_stride_a, int add_noise, uint64_t seed, uint32_t act_call) {
+                                    int H, int dU, int sol_stride_a, int add_noise, uint64_t seed, const uint32_t* act_ctr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A * dU) return;
   const int a = i / dU, u = i % dU;
   float v = sol[a * sol_stride_a + u];
   if (add_noise) {
-    const Philox4 r = draw_block(seed, act_call, STREAM_EXPLORE, 0, a, u);
+    const Philox4 r = draw_block(seed, *act_ctr, STREAM_EXPLORE, 0, a, u);
     const float d = __fsub_rn(lb[u], ub[u]);
     const float var = __fmul_rn(__fdiv_rn(__fmul_rn(d, d), 16.0f), 0.05f);
     const float mean = __fdiv_rn(__fadd_rn(ub[u], lb[u]), 2.0f);
@@ -74,7 +81,9 @@ __global__ void first_action_kernel(const float* sol, float* action, const float
 // Global Philox row = p_global * A + a.
 struct SampleArgs {
   float* samples; float* penalty; const float* mean; const float* var; const float* lb; const float* ub;
-  int P_local, p0, A, H, dU; uint64_t seed; uint32_t act_call, iter;
+  int P_local, p0, A, H, dU; uint64_t seed;
+  const uint32_t* act_ctr;   // act() calls completed so far, on the device: a captured graph replays with a fresh Philox counter
+  uint32_t iter;
   float ck;   // SPSA perturbation size
   float* raw_trace;  // optional: un-clipped draws of this iteration (PI2), for oracle injection
   const float* inject;  // optional: this iteration's standard variates [P, A, H*dU] by GLOBAL row, instead of Philox
@@ -87,7 +96,7 @@ __global__ void cem_sample_kernel(const SampleArgs s) {
   if (gid >= static_cast<int64_t>(s.P_local) * s.A * nb) return;
   const int blk = gid % nb; const int64_t pa = gid / nb;
   const int a = pa % s.A; const int p = pa / s.A;
-  const Philox4 r = draw_block(s.seed, s.act_call, STREAM_SAMPLES, s.iter, (s.p0 + p) * s.A + a, blk);
+  const Philox4 r = draw_block(s.seed, *s.act_ctr, STREAM_SAMPLES, s.iter, (s.p0 + p) * s.A + a, blk);
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
   for (int j = 0; j < 4; ++j) {
     const int e = 4 * blk + j;
@@ -109,7 +118,7 @@ __global__ void pi2_sample_kernel(const SampleArgs s, float* raw_excess_sq) {
   if (gid >= static_cast<int64_t>(s.P_local) * s.A * nb) return;
   const int blk = gid % nb; const int64_t pa = gid / nb;
   const int a = pa % s.A; const int p = pa / s.A;
-  const Philox4 r = draw_block(s.seed, s.act_call, STREAM_SAMPLES, s.iter, (s.p0 + p) * s.A + a, blk);
+  const Philox4 r = draw_block(s.seed, *s.act_ctr, STREAM_SAMPLES, s.iter, (s.p0 + p) * s.A + a, blk);
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
   for (int j = 0; j < 4; ++j) {
     const int e = 4 * blk + j;
@@ -131,7 +140,7 @@ __global__ void rs_sample_kernel(const SampleArgs s) {
   if (gid >= static_cast<int64_t>(s.P_local) * s.A * nb) return;
   const int blk = gid % nb; const int64_t pa = gid / nb;
   const int a = pa % s.A; const int p = pa / s.A;
-  const Philox4 r = draw_block(s.seed, s.act_call, STREAM_SAMPLES, s.iter, (s.p0 + p) * s.A + a, blk);
+  const Philox4 r = draw_block(s.seed, *s.act_ctr, STREAM_SAMPLES, s.iter, (s.p0 + p) * s.A + a, blk);
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
   for (int j = 0; j < 4; ++j) {
     const int e = 4 * blk + j;
@@ -149,7 +158,7 @@ __global__ void spsa_sample_kernel(const SampleArgs s, float* raw_excess_sq) {
   if (gid >= half * nb) return;
   const int blk = gid % nb; const int64_t pa = gid / nb;
   const int a = pa % s.A; const int p = pa / s.A;
-  const Philox4 r = draw_block(s.seed, s.act_call, STREAM_SAMPLES, s.iter, (s.p0 + p) * s.A + a, blk);
+  const Philox4 r = draw_block(s.seed, *s.act_ctr, STREAM_SAMPLES, s.iter, (s.p0 + p) * s.A + a, blk);
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
   for (int j = 0; j < 4; ++j) {
     const int e = 4 * blk + j;
@@ -179,11 +188,16 @@ __global__ void penalty_kernel(const float* excess_sq, float* penalty, int64_t r
   if (lane == 0) { const float n = sqrtf(acc); penalty[row] = __fmul_rn(n, n); }
 }
 
-// ---- CEM local top-E -> partial message.  One CTA per agent.
+// ---- CEM local top-E -> partial message.  One CTA per (agent, population slice): gridDim.y slices of the local rows,
+// each with its own message (slice y at partial + y * slice_stride); the merge kernel treats slices like ranks.
 // partial layout per agent: E records of (reward, global_p bits, seq[HU]).
 __global__ void __launch_bounds__(SEL_THREADS) topk_partial_kernel(const float* returns, const float* samples,
-                                                                   float* partial, int P_local, int p0, int A,
-                                                                   int HU, int E, int use_cache) {
+                                                                   float* partial, int P_all, int p0_all, int A,
+                                                                   int HU, int E, int use_cache, int64_t slice_stride) {
+  const int n_slices = static_cast<int>(gridDim.y), y = static_cast<int>(blockIdx.y);
+  const int pb = static_cast<int>(static_cast<int64_t>(P_all) * y / n_slices), pe = static_cast<int>(static_cast<int64_t>(P_all) * (y + 1) / n_slices);
+  const int P_local = pe - pb, p0 = p0_all + pb;
+  returns += static_cast<size_t>(pb) * A; samples += static_cast<size_t>(pb) * A * HU; partial += y * slice_stride;
   __shared__ int hist[256];
   __shared__ int misc[40];
   __shared__ uint32_t keys[SEL_MAX_K];
@@ -396,7 +410,7 @@ __global__ void argmax_merge_kernel(const float* partials, int world, int HU, fl
 
 // ---- SPSA partial: sum_p (r+ - r-) / (2 ck delta) per (a,e) (spsa.py:98-103); delta regenerated
 __global__ void spsa_partial_kernel(const float* returns, float* partial, int P_local, int p0, int A, int HU,
-                                    float ck, uint64_t seed, uint32_t act_call, uint32_t iter, const float* inject) {
+                                    float ck, uint64_t seed, const uint32_t* act_ctr, uint32_t iter, const float* inject) {
   // one warp per (a, e): lanes stride the population, fixed-order tree reduction
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= A * HU) return;
@@ -404,7 +418,7 @@ __global__ void spsa_partial_kernel(const float* returns, float* partial, int P_
   const int64_t half = static_cast<int64_t>(P_local) * A;
   float acc = 0.0f;
   for (int p = lane; p < P_local; p += 32) {
-    const Philox4 r = draw_block(seed, act_call, STREAM_SAMPLES, iter, (p0 + p) * A + a, e >> 2);
+    const Philox4 r = draw_block(seed, *act_ctr, STREAM_SAMPLES, iter, (p0 + p) * A + a, e >> 2);
     const uint32_t word = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
     const float delta = inject ? inject[(static_cast<int64_t>(p0 + p) * A + a) * HU + e] : ((word >> 31) ? 1.0f : -1.0f);
     const float diff = __fsub_rn(returns[p * A + a], returns[half + p * A + a]);
@@ -447,10 +461,10 @@ __global__ void pso_pbest_r_kernel(const float* rewards, float* pbr, int64_t row
 }
 // velocity / position update (pso.py:107-111); r1, r2: ONE N(0,1) scalar each per iteration
 __global__ void pso_move_kernel(float* x, float* v, const float* pbx, const float* gbx, int64_t n, int AHU, float w,
-                                float c1, float c2, uint64_t seed, uint32_t act_call, uint32_t iter, float* r_record) {
+                                float c1, float c2, uint64_t seed, const uint32_t* act_ctr, uint32_t iter, float* r_record) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const Philox4 r = draw_block(seed, act_call, STREAM_PSO_R, iter, 0, 0);
+  const Philox4 r = draw_block(seed, *act_ctr, STREAM_PSO_R, iter, 0, 0);
   const float r1 = std_normal(r.x), r2 = std_normal(r.y);
   if (i == 0 && r_record) { r_record[2 * iter] = r1; r_record[2 * iter + 1] = r2; }   // inspection: get_tensor("pso_r")
   const float xi = x[i];
@@ -463,8 +477,9 @@ __global__ void pso_move_kernel(float* x, float* v, const float* pbx, const floa
 // _optimize: x ~ truncnorm(shift(gbest), sqrt(cvar(UNSHIFTED gbest))) (pso.py:116-138)
 __global__ void pso_seed_kernel(float* x, float* v, float* pbx, const float* gbx, const float* var0, const float* lb,
                                 const float* ub, int P_local, int p0, int A, int H, int dU, float v0frac, int mode,
-                                uint64_t seed, uint32_t act_call) {
+                                uint64_t seed, const uint32_t* act_ctr) {
   const int HU = H * dU;
+  const uint32_t act_call = *act_ctr;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<int64_t>(P_local) * A * HU) return;
   const int e = i % HU; const int64_t pa = i / HU; const int a = pa % A; const int p = pa / A;
@@ -538,11 +553,13 @@ void launch_penalty(const float* excess_sq, float* penalty, int64_t rows, int HU
   penalty_kernel<<<grid_for(rows * 32, 256), 256, 0, st>>>(excess_sq, penalty, rows, HU);
 }
 void launch_topk_partial(const float* returns, const float* samples, float* partial, int P_local, int p0, int A, int HU, int E,
-                         cudaStream_t st) {
+                         cudaStream_t st, int n_slices, int64_t slice_stride) {
   // opt in to > 48 KB of dynamic shared memory (per device and function: set on every launch, it is a host-side table write)
   cudaFuncSetAttribute(topk_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  const int use_cache = (P_local > 0 && P_local <= 16384) ? 1 : 0;   // 64 KB of dynamic shared memory at most
-  topk_partial_kernel<<<A, SEL_THREADS, use_cache ? P_local * sizeof(uint32_t) : 0, st>>>(returns, samples, partial, P_local, p0, A, HU, E, use_cache);
+  const int per = (P_local + n_slices - 1) / n_slices + 1;
+  const int use_cache = (P_local > 0 && per <= 16384) ? 1 : 0;   // 64 KB of dynamic shared memory at most
+  topk_partial_kernel<<<dim3(A, n_slices), SEL_THREADS, use_cache ? per * sizeof(uint32_t) : 0, st>>>(returns, samples, partial, P_local, p0, A, HU, E,
+                                                                                                    use_cache, slice_stride);
 }
 }  // namespace bbmpc
 
@@ -561,6 +578,18 @@ static int partial_floats(const bbmpc_opt* o) {
 }
 
 static int set_shard(bbmpc_opt* o, int rank, int world);
+// population slices of the unsharded CEM top-E: candidates of all slices (slices x E) must fit the merge kernel's sort
+static int cem_slice_count(const bbmpc_opt* o) {
+  int s = o->P_local / 1024;
+  const int cap = SEL_MAX_K / (o->cfg.num_elite > 0 ? o->cfg.num_elite : 1);
+  if (s > 8) s = 8;
+  if (s > cap) s = cap;
+  return s < 1 ? 1 : s;
+}
+static void opt_graph_drop(bbmpc_opt* o) {
+  if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
+  o->graph_exec = nullptr; o->graph_warm = 0; o->graph_noise = -1;
+}
 
 extern "C" {
 
@@ -587,10 +616,12 @@ int bbmpc_opt_create(bbmpc_ctx* ctx, const bbmpc_opt_config* cfg, bbmpc_opt** ou
   A_(dalloc(o, &o->d_state, A * dS)); A_(dalloc(o, &o->d_mean, o->AHU)); A_(dalloc(o, &o->d_var, o->AHU));
   A_(dalloc(o, &o->d_prev, o->AHU)); A_(dalloc(o, &o->d_var0, o->AHU));
   A_(dalloc(o, &o->d_action, A * dU)); A_(dalloc(o, &o->d_next, A * dS)); A_(dalloc(o, &o->d_reward, A));
+  A_(dalloc(o, &o->d_act_ctr, 1));
   if (cfg->kind == BBMPC_OPT_PSO) { A_(dalloc(o, &o->d_gbx, o->AHU)); A_(dalloc(o, &o->d_gbr, A)); A_(dalloc(o, &o->d_sol, A * dU)); A_(dalloc(o, &o->d_pso_r, 128)); }
   if (rc == BBMPC_OK && cudaMallocHost(reinterpret_cast<void**>(&o->h_pinned), (A * dS * 2 + A * dU + A) * sizeof(float)) != cudaSuccess)
     rc = fail(ctx, BBMPC_ENOMEM, "cudaMallocHost failed");
   if (rc != BBMPC_OK) { bbmpc_opt_destroy(o); return rc; }
+  cudaMemset(o->d_act_ctr, 0, sizeof(uint32_t));
   cudaMemcpy(o->d_lb, cfg->lb_host, dU * sizeof(float), cudaMemcpyHostToDevice);
   cudaMemcpy(o->d_ub, cfg->ub_host, dU * sizeof(float), cudaMemcpyHostToDevice);
   fill_midpoint_kernel<<<grid_for(o->AHU, 256), 256>>>(o->d_prev, o->d_lb, o->d_ub, o->AHU, dU);
@@ -612,6 +643,8 @@ void bbmpc_opt_destroy(bbmpc_opt* o) {
   if (!o) return;
   cudaSetDevice(o->ctx->device);
   cudaDeviceSynchronize();
+  if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
+  if (o->graph_stream) cudaStreamDestroy(o->graph_stream);
   for (void* p : o->p2p_opened) cudaIpcCloseMemHandle(p);
   for (void* p : o->owned) cudaFree(p);
   if (o->h_pinned) cudaFreeHost(o->h_pinned);
@@ -623,6 +656,7 @@ void bbmpc_opt_destroy(bbmpc_opt* o) {
 // (Re)allocates the population-sized buffers for this rank's slice.
 static int set_shard(bbmpc_opt* o, int rank, int world) {
   bbmpc_ctx* ctx = o->ctx;
+  opt_graph_drop(o);   // the population-sized buffers are reallocated below
   const int P = o->cfg.population_size, A = o->cfg.num_agents;
   if (world < 1 || rank < 0 || rank >= world) return fail(ctx, BBMPC_EINVAL, "bad shard %d/%d", rank, world);
   if (world > 1 && o->cfg.kind == BBMPC_OPT_CEM && world * o->cfg.num_elite > SEL_MAX_K)
@@ -637,7 +671,7 @@ static int set_shard(bbmpc_opt* o, int rank, int world) {
   auto A_ = [&](int r) { if (rc == BBMPC_OK) rc = r; };
   // (old population buffers stay in `owned` until destroy; resharding is a setup-time operation)
   A_(dalloc(o, &o->d_samples, rows * o->HU)); A_(dalloc(o, &o->d_returns, rows)); A_(dalloc(o, &o->d_penalty, rows));
-  A_(dalloc(o, &o->d_partial, static_cast<size_t>(partial_floats(o))));
+  A_(dalloc(o, &o->d_partial, static_cast<size_t>(partial_floats(o)) * (o->cfg.kind == BBMPC_OPT_CEM ? 8 : 1)));
   if (o->cfg.kind == BBMPC_OPT_PI2 || o->cfg.kind == BBMPC_OPT_SPSA || o->cfg.kind == BBMPC_OPT_PSO)
     A_(dalloc(o, &o->d_work, rows * o->HU));
   if (o->cfg.kind == BBMPC_OPT_CMAES) A_(cmaes_set_shard(o));
@@ -681,7 +715,7 @@ int bbmpc_opt_reset(bbmpc_opt* o, void* stream) {
       const int64_t n = static_cast<int64_t>(o->P_local) * o->AHU;
       pso_seed_kernel<<<grid_for(n, 256), 256, 0, st>>>(o->d_samples, o->d_v, o->d_pbx, o->d_gbx, o->d_var0, o->d_lb, o->d_ub,
                                                         o->P_local, o->p0, o->cfg.num_agents, o->cfg.planning_horizon, dU,
-                                                        o->cfg.initial_velocity_fraction, 0, ctx->seed, o->act_call);
+                                                        o->cfg.initial_velocity_fraction, 0, ctx->seed, o->d_act_ctr);
       BB_LAUNCH_CHECK(ctx);
       const int64_t rows = static_cast<int64_t>(o->P_local) * o->cfg.num_agents;
       fill_kernel<<<grid_for(rows, 256), 256, 0, st>>>(o->d_pbr, -INFINITY, rows); BB_LAUNCH_CHECK(ctx);
@@ -727,13 +761,14 @@ int bbmpc_opt_iter_local(bbmpc_opt* o, int iter, float* partial_out, void* strea
   bbmpc_ctx* ctx = o->ctx;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!o->began) return opt_fail(o, BBMPC_ESTATE, "iter_local before begin");
+  NvtxRange nvtx_range("bbmpc:sample+rollout+local_refit");
   BB_CUDA(ctx, cudaSetDevice(ctx->device));
   const bbmpc_opt_config& c = o->cfg;
   const int A = c.num_agents, H = c.planning_horizon, dU = c.dU, HU = o->HU;
   float* partial = partial_out ? partial_out : o->d_partial;
   if (c.kind == BBMPC_OPT_CMAES) return cmaes_iter_local(o, iter, partial, st);
   SampleArgs s{o->d_samples, o->d_penalty, o->d_mean, o->d_var, o->d_lb, o->d_ub, o->P_local, o->p0, A, H, dU,
-               ctx->seed, o->act_call, static_cast<uint32_t>(iter), 0.0f, nullptr, nullptr};
+               ctx->seed, o->d_act_ctr, static_cast<uint32_t>(iter), 0.0f, nullptr, nullptr};
   {  // injected standard variates: one block of [P, A, H*dU] per iteration since bbmpc_opt_set_draw_injection
     const int64_t blk = static_cast<int64_t>(c.population_size) * A * HU;
     if (o->inject && c.kind != BBMPC_OPT_PSO) {
@@ -777,11 +812,17 @@ int bbmpc_opt_iter_local(bbmpc_opt* o, int iter, float* partial_out, void* strea
     }
     if (trace_slot && c.kind != BBMPC_OPT_PI2)
       BB_CUDA(ctx, cudaMemcpyAsync(trace_slot, o->d_samples, per_iter * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (int rc = rollout_dispatch(ctx, o->d_state, o->d_samples, o->d_returns, penalty, static_cast<int>(rows), A, H, st)) return rc;
+    {
+      NvtxRange nvtx_rollout("bbmpc:rollout");
+      if (int rc = rollout_dispatch(ctx, o->d_state, o->d_samples, o->d_returns, penalty, static_cast<int>(rows), A, H, st)) return rc;
+    }
   }
   switch (c.kind) {
     case BBMPC_OPT_CEM:
-      launch_topk_partial(o->d_returns, o->d_samples, partial, o->P_local, o->p0, A, HU, c.num_elite, st);
+      // unsharded, internal message buffer: the local rows are cut into slices, one CTA each (a single CTA scanning
+      // 10 000 returns took 34 us per iteration); bbmpc_opt_iter_merge ranks the slices' candidates like ranks'
+      o->cem_slices = (!partial_out && o->world == 1) ? cem_slice_count(o) : 1;
+      launch_topk_partial(o->d_returns, o->d_samples, partial, o->P_local, o->p0, A, HU, c.num_elite, st, o->cem_slices, partial_floats(o));
       break;
     case BBMPC_OPT_PI2:
       pi2_partial_kernel<<<A, 1024, 0, st>>>(o->d_returns, o->d_samples, partial, o->P_local, A, HU, c.lamda); BB_LAUNCH_CHECK(ctx);
@@ -794,7 +835,7 @@ int bbmpc_opt_iter_local(bbmpc_opt* o, int iter, float* partial_out, void* strea
     case BBMPC_OPT_SPSA:
       spsa_partial_kernel<<<grid_for(static_cast<int64_t>(A) * HU * 32, 256), 256, 0, st>>>(
           o->d_returns, partial, o->P_local, o->p0, A, HU, c.noise_parameter / powf(static_cast<float>(iter) + 1.0f, c.gamma),
-          ctx->seed, o->act_call, static_cast<uint32_t>(iter), s.inject);
+          ctx->seed, o->d_act_ctr, static_cast<uint32_t>(iter), s.inject);
       break;
     case BBMPC_OPT_PSO: {
       pso_pbest_kernel<<<grid_for(rows * HU, 256), 256, 0, st>>>(o->d_samples, o->d_returns, o->d_pbx, o->d_pbr, rows, HU); BB_LAUNCH_CHECK(ctx);
@@ -813,6 +854,7 @@ int bbmpc_opt_iter_merge(bbmpc_opt* o, int iter, const float* partials, int worl
   bbmpc_ctx* ctx = o->ctx;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!o->began) return opt_fail(o, BBMPC_ESTATE, "iter_merge before begin");
+  NvtxRange nvtx_range("bbmpc:merge+refit");
   if (world < 1) return opt_fail(o, BBMPC_EINVAL, "world < 1");
   BB_CUDA(ctx, cudaSetDevice(ctx->device));
   const bbmpc_opt_config& c = o->cfg;
@@ -823,7 +865,7 @@ int bbmpc_opt_iter_merge(bbmpc_opt* o, int iter, const float* partials, int worl
   switch (c.kind) {
     case BBMPC_OPT_CEM:
       if (world * c.num_elite > SEL_MAX_K) return opt_fail(o, BBMPC_EINVAL, "world*num_elite exceeds 1024");
-      cem_refit_kernel<<<A, SEL_THREADS, 0, st>>>(in, world, A, HU, c.num_elite, c.alpha, o->d_mean, o->d_var, stride);
+      cem_refit_kernel<<<A, SEL_THREADS, 0, st>>>(in, (!partials && world == 1) ? o->cem_slices : world, A, HU, c.num_elite, c.alpha, o->d_mean, o->d_var, stride);
       break;
     case BBMPC_OPT_PI2:
       pi2_merge_kernel<<<A, 256, 0, st>>>(in, world, A, HU, c.lamda, o->d_mean, stride);
@@ -842,7 +884,7 @@ int bbmpc_opt_iter_merge(bbmpc_opt* o, int iter, const float* partials, int worl
       const int64_t n = static_cast<int64_t>(o->P_local) * o->AHU;
       if (n > 0)
         pso_move_kernel<<<grid_for(n, 256), 256, 0, st>>>(o->d_samples, o->d_v, o->d_pbx, o->d_gbx, n, o->AHU, c.w, c.c1, c.c2,
-                                                          ctx->seed, o->act_call, static_cast<uint32_t>(iter),
+                                                          ctx->seed, o->d_act_ctr, static_cast<uint32_t>(iter),
                                                           iter < 64 ? o->d_pso_r : nullptr);
       else return BBMPC_OK;
       break;
@@ -858,6 +900,7 @@ int bbmpc_opt_finish(bbmpc_opt* o, int add_noise, float* action, float* next_sta
   bbmpc_ctx* ctx = o->ctx;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!o->began) return opt_fail(o, BBMPC_ESTATE, "finish before begin");
+  NvtxRange nvtx_range("bbmpc:finish(first action, predict, reward)");
   BB_CUDA(ctx, cudaSetDevice(ctx->device));
   const bbmpc_opt_config& c = o->cfg;
   const int A = c.num_agents, H = c.planning_horizon, dU = c.dU, dS = c.dS, HU = o->HU;
@@ -871,7 +914,7 @@ int bbmpc_opt_finish(bbmpc_opt* o, int add_noise, float* action, float* next_sta
       const int64_t n = static_cast<int64_t>(o->P_local) * o->AHU;
       if (n > 0) {
         pso_seed_kernel<<<grid_for(n, 256), 256, 0, st>>>(o->d_samples, o->d_v, o->d_pbx, o->d_gbx, o->d_var0, o->d_lb, o->d_ub,
-                                                          o->P_local, o->p0, A, H, dU, c.initial_velocity_fraction, 1, ctx->seed, o->act_call);
+                                                          o->P_local, o->p0, A, H, dU, c.initial_velocity_fraction, 1, ctx->seed, o->d_act_ctr);
         BB_LAUNCH_CHECK(ctx);
         const int64_t rows = static_cast<int64_t>(o->P_local) * A;
         fill_kernel<<<grid_for(rows, 256), 256, 0, st>>>(o->d_pbr, -INFINITY, rows); BB_LAUNCH_CHECK(ctx);
@@ -885,23 +928,21 @@ int bbmpc_opt_finish(bbmpc_opt* o, int add_noise, float* action, float* next_sta
   float* next_out = next_state ? next_state : o->d_next;
   float* rew_out = reward ? reward : o->d_reward;
   first_action_kernel<<<grid_for(A * dU, 128), 128, 0, st>>>(sol, act_out, o->d_lb, o->d_ub, A, H, dU, sol_stride, add_noise,
-                                                            ctx->seed, o->act_call);
+                                                            ctx->seed, o->d_act_ctr);
   BB_LAUNCH_CHECK(ctx);
   // predict_next_state + evaluate_next_reward on the A executed actions (optimizer_base.py:91-94)
   StepIO io{o->d_state, act_out, nullptr, next_out, rew_out, nullptr, A, 3};
   if (int rc = launch_step_simt(ctx, io, st)) return rc;
+  act_ctr_bump_kernel<<<1, 1, 0, st>>>(o->d_act_ctr); BB_LAUNCH_CHECK(ctx);
   o->act_call++;
   o->began = false;
   (void)dS;
   return BBMPC_OK;
 }
 
-int bbmpc_opt_call(bbmpc_opt* o, const float* state, int time_step, int add_noise, float* action, float* next_state,
-                   float* reward, void* stream) {
-  if (!o) return BBMPC_EINVAL;
-  if (o->world != 1 && !o->p2p_on)
-    return opt_fail(o, BBMPC_ESTATE, "bbmpc_opt_call on a sharded optimizer without a peer-memory exchange: use begin/iter_local/iter_merge/finish");
-  if (int rc = bbmpc_opt_begin(o, state, time_step, stream)) return rc;
+// The kernels of one act() on the handle's own buffers (state in d_state; results in d_action / d_next / d_reward).
+static int opt_call_body(bbmpc_opt* o, int time_step, int add_noise, void* stream) {
+  if (int rc = bbmpc_opt_begin(o, o->d_state, time_step, stream)) return rc;
   const int n = bbmpc_opt_num_iterations(o);
   for (int it = 0; it < n; ++it) {
     if (o->p2p_on) {
@@ -921,7 +962,82 @@ int bbmpc_opt_call(bbmpc_opt* o, const float* state, int time_step, int add_nois
     if (int rc = bbmpc_opt_iter_local(o, it, nullptr, stream)) return rc;
     if (int rc = bbmpc_opt_iter_merge(o, it, nullptr, 1, stream)) return rc;
   }
-  return bbmpc_opt_finish(o, add_noise, action, next_state, reward, stream);
+  return bbmpc_opt_finish(o, add_noise, o->d_action, o->d_next, o->d_reward, stream);
+}
+
+
+// optimizers/optimizer_base.py:55-56: the reference runs one tf.function graph per act().  Here the ~25 kernels of an act()
+// are captured once (after two eager calls that size every scratch buffer) into a CUDA graph over the handle's own buffers
+// and replayed: one launch per act(), no launch gaps between the small kernels.  The Philox act-call counter lives on the
+// device (bumped by the last kernel), so a replay draws fresh samples.  Not captured: sharded handles (their sequence
+// numbers are launch arguments), calls with a sample trace / draw injection / rollout profiling, BBMPC_NO_GRAPH=1.
+int bbmpc_opt_call(bbmpc_opt* o, const float* state, int time_step, int add_noise, float* action, float* next_state,
+                   float* reward, void* stream) {
+  if (!o) return BBMPC_EINVAL;
+  bbmpc_ctx* ctx = o->ctx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (o->world != 1 && !o->p2p_on)
+    return opt_fail(o, BBMPC_ESTATE, "bbmpc_opt_call on a sharded optimizer without a peer-memory exchange: use begin/iter_local/iter_merge/finish");
+  if (!state) return opt_fail(o, BBMPC_EINVAL, "state is NULL");
+  BB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int A = o->cfg.num_agents, dS = o->cfg.dS, dU = o->cfg.dU;
+  if (state != o->d_state)
+    BB_CUDA(ctx, cudaMemcpyAsync(o->d_state, state, A * dS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const bool no_graph = getenv("BBMPC_NO_GRAPH") != nullptr;
+  const bool graphable = !no_graph && o->world == 1 && !o->trace && !o->inject && !ctx->prof_on && ctx->model.set && ctx->reward_id &&
+                         o->cfg.kind != BBMPC_OPT_CMAES;   // (cuSOLVER's syevd is not capturable)
+  int rc = BBMPC_OK;
+  if (!graphable) {
+    rc = opt_call_body(o, time_step, add_noise, stream);
+  } else {
+    if (o->graph_exec && (o->graph_epoch != ctx->epoch || o->graph_noise != add_noise)) opt_graph_drop(o);
+    if (o->graph_exec) {
+      BB_CUDA(ctx, cudaGraphLaunch(o->graph_exec, st));
+      o->act_call++;
+      ctx->launches += o->graph_launches;
+    } else if (o->graph_warm < 2) {
+      ++o->graph_warm;                      // eager: scratch buffers are (re)allocated on the first calls
+      rc = opt_call_body(o, time_step, add_noise, stream);
+    } else {
+      // Capture on a stream of our own (the caller's may be the legacy default stream, which cannot be captured); the
+      // instantiated graph is launched into the caller's stream.
+      const uint64_t before = ctx->launches;
+      const uint32_t act_before = o->act_call;
+      cudaGraph_t graph = nullptr;
+      bool ok = true;
+      if (!o->graph_stream) ok = cudaStreamCreateWithFlags(&o->graph_stream, cudaStreamNonBlocking) == cudaSuccess;
+      ok = ok && cudaStreamBeginCapture(o->graph_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        rc = opt_call_body(o, time_step, add_noise, o->graph_stream);
+        const cudaError_t ce = cudaStreamEndCapture(o->graph_stream, &graph);
+        ok = rc == BBMPC_OK && ce == cudaSuccess && graph != nullptr;
+      }
+      cudaGraphExec_t exec = nullptr;
+      if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+      o->act_call = act_before;               // the captured body advanced the host mirrors without running
+      o->began = false;
+      if (ok) {
+        o->graph_exec = exec; o->graph_epoch = ctx->epoch; o->graph_noise = add_noise;
+        o->graph_launches = ctx->launches - before;
+        ctx->launches = before;
+        BB_CUDA(ctx, cudaGraphLaunch(o->graph_exec, st));
+        o->act_call++;
+        ctx->launches += o->graph_launches;
+        rc = BBMPC_OK;
+      } else {
+        cudaGetLastError();
+        ctx->launches = before;
+        o->graph_warm = -1000000;             // this configuration cannot be captured: stay eager
+        rc = opt_call_body(o, time_step, add_noise, stream);
+      }
+    }
+  }
+  if (rc != BBMPC_OK) return rc;
+  if (action && action != o->d_action) BB_CUDA(ctx, cudaMemcpyAsync(action, o->d_action, A * dU * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (next_state && next_state != o->d_next) BB_CUDA(ctx, cudaMemcpyAsync(next_state, o->d_next, A * dS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (reward && reward != o->d_reward) BB_CUDA(ctx, cudaMemcpyAsync(reward, o->d_reward, A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return BBMPC_OK;
 }
 
 int bbmpc_opt_call_host(bbmpc_opt* o, const float* state_host, int time_step, int add_noise, float* action_host,

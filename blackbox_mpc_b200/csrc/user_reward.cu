@@ -173,11 +173,13 @@ extern "C" int bbmpc_reward_set_nvrtc(bbmpc_ctx* ctx, const char* cuda_source) {
   if (cudaSetDevice(ctx->device) != cudaSuccess) return bbmpc::fail(ctx, BBMPC_ECUDA, "cudaSetDevice failed");
   if (ctx->user_reward_src == cuda_source && ctx->user_reward_traj && ctx->user_reward_dS == ctx->model.dS &&
       ctx->user_reward_dU == ctx->model.dU) {
+    if (ctx->reward_id != BBMPC_REWARD_USER) ctx->epoch++;
     ctx->reward_id = BBMPC_REWARD_USER;
     return BBMPC_OK;   // already compiled for this context
   }
   if (int rc = bbmpc::user_reward_compile(ctx, cuda_source)) return rc;
   ctx->user_reward_src = cuda_source;
   ctx->reward_id = BBMPC_REWARD_USER;
+  ctx->epoch++;
   return BBMPC_OK;
 }

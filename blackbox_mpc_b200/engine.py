@@ -52,6 +52,10 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.bbmpc_launch_count(self.handle))
 
+    @property
+    def last_rollout_kernel(self) -> str:
+        return (self.lib.bbmpc_last_rollout_kernel(self.handle) or b"").decode()
+
     def profile_enable(self, on: bool = True) -> None:
         self.check(self.lib.bbmpc_profile_enable(self.handle, 1 if on else 0))
 

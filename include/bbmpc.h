@@ -78,6 +78,8 @@ int bbmpc_set_precision(bbmpc_ctx* ctx, int prec);
 int bbmpc_get_effective_precision(const bbmpc_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t bbmpc_launch_count(const bbmpc_ctx* ctx);
+/* Name of the kernel the last rollout launched (rollout_pipe_kernel / rollout_tc_kernel / rollout_simt_kernel). */
+const char* bbmpc_last_rollout_kernel(const bbmpc_ctx* ctx);
 /* Rollout-kernel timing for bench.py's roofline: while enabled, every rollout launch is bracketed
  * by a CUDA event pair on its own stream.  bbmpc_profile_read synchronises on the recorded events,
  * returns the summed device time (ms) and the number of launches, and clears the record. */
