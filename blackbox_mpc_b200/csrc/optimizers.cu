@@ -579,8 +579,10 @@ static int partial_floats(const bbmpc_opt* o) {
 
 static int set_shard(bbmpc_opt* o, int rank, int world);
 // population slices of the unsharded CEM top-E: candidates of all slices (slices x E) must fit the merge kernel's sort
+// (measured at P = 10 000: 8 slices take the selection from 34 to 29 us but the 400-candidate merge from 17 to 27 us: the
+// kernels are bound by their ~25 block-wide phases, not by the scan, so slices only pay for much larger populations)
 static int cem_slice_count(const bbmpc_opt* o) {
-  int s = o->P_local / 1024;
+  int s = o->P_local / 32768;
   const int cap = SEL_MAX_K / (o->cfg.num_elite > 0 ? o->cfg.num_elite : 1);
   if (s > 8) s = 8;
   if (s > cap) s = cap;

@@ -47,9 +47,18 @@ def _drive(opts, w, world):
     return per_iter, acts
 
 
-def test_cmaes_matches_oracle(cuda_device):
-    w = _workload()
+def _workload_c5(P=2000, iters=2):
+    """BASELINE C5 shape: HalfCheetah 3x200 MLP, H = 50, dU = 6 -> N = 300 search dimensions, 50 elites."""
+    w = workloads.make("C5", population_size=P, bias_scale=0.1)
+    w.max_iterations = iters
+    return w
+
+
+@pytest.mark.parametrize("which", ["small", "c5_n300"])
+def test_cmaes_matches_oracle(cuda_device, which):
+    w = _workload() if which == "small" else _workload_c5()
     N = w.num_agents * w.planning_horizon * w.dU
+    assert which == "small" or N == 300
     policy = workloads.build_policy(w, precision="fp32")
     opt = policy._optimizer
     opt._ensure_handle()
@@ -70,11 +79,14 @@ def test_cmaes_matches_oracle(cuda_device):
     o = helpers.oracle_optimizer(w, "CMA-ES", dtype=torch.float64, eig_fn=lambda C: eigs.pop(0))
     draws = oracle.InjectedDraws({"cmaes.z": zs}, dtype=torch.float64)
     ref_action = o._optimize(torch.from_numpy(w.state).double(), 0, draws)
+    # N = 300: sums of 300 fp32 products per sample and 50 x 300 x 300 rank-mu terms; elite membership is exact unless two
+    # returns tie within fp32 noise, the statistics agree to fp32 accumulation error
+    rtol, atol = (2e-4, 2e-5) if which == "small" else (1e-3, 2e-4)
     for it, (st, ref) in enumerate(zip(per_iter, o.trace)):
         for key, rk in (("m", "m"), ("sigma", "sigma"), ("p_sigma", "p_sigma"), ("p_C", "p_C"), ("C", "C")):
-            np.testing.assert_allclose(st[key].numpy().ravel(), ref[rk].numpy().ravel(), rtol=2e-4, atol=2e-5,
+            np.testing.assert_allclose(st[key].numpy().ravel(), ref[rk].numpy().ravel(), rtol=rtol, atol=atol,
                                        err_msg=f"iteration {it}: {key}")
-    np.testing.assert_allclose(acts[0].numpy(), ref_action.numpy(), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(acts[0].numpy(), ref_action.numpy(), rtol=rtol, atol=atol)
 
 
 def test_cmaes_shard_invariance(cuda_device):

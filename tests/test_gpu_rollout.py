@@ -167,3 +167,60 @@ def test_rollout_shapes_against_oracle(cuda_device, layers, acts, n_members, dS,
     got = ev(state, actions, 0).cpu().numpy()
     ref = helpers.oracle_evaluator(w, torch.float64)(state.double(), actions.double(), 0).numpy()
     helpers.compare_returns(got, ref, max_jump_frac=0.05, **TOL["bf16x3"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_unnormalised_mlp_rollout(cuda_device, precision):
+    """is_normalized=False with a learned MLP: process_input is the raw concat [s, a], process_output is s + y
+    (system_dynamics_handler.py:125-126,160-161 of the reference).  Weights scaled down so that the raw recurrence stays bounded."""
+    import oracle as ref
+    from blackbox_mpc_b200.dynamics_functions.deterministic_mlp import DeterministicMLP
+    from blackbox_mpc_b200.dynamics_handlers.system_dynamics_handler import SystemDynamicsHandler
+    from blackbox_mpc_b200.spaces import Box
+    from blackbox_mpc_b200.trajectory_evaluators.deterministic import DeterministicTrajectoryEvaluator
+    from blackbox_mpc_b200.utils import halfcheetah
+    P = 300
+    w = workloads.make("C3", population_size=P, planning_horizon=12, bias_scale=0.05)
+    ws = [x * np.float32(0.3) for x in w.weights[0]]
+    bs = [x * np.float32(0.3) for x in w.biases[0]]
+    mlp = DeterministicMLP(w.layers, w.activations)
+    mlp.set_weights(ws, bs)
+    act_space, obs_space = Box(w.lb, w.ub), Box(-np.ones(w.dS, np.float32), np.ones(w.dS, np.float32))
+    handler = SystemDynamicsHandler(act_space, obs_space, dynamics_function=mlp, true_model=False, is_normalized=False, precision=precision)
+    ev = DeterministicTrajectoryEvaluator(reward_function=halfcheetah.reward_function, system_dynamics_handler=handler)
+    assert ev.engine().effective_precision == precision
+    actions = helpers.random_actions(w, P, seed=13)
+    state = torch.from_numpy(w.state)
+    got = ev(state, actions, 0).cpu().numpy()
+    o_handler = ref.Handler(ref.MLP([torch.from_numpy(x) for x in ws], [torch.from_numpy(x) for x in bs], w.activations),
+                            true_model=False, is_normalized=False, dtype=torch.float64)
+    o_ev = ref.Evaluator(ref.halfcheetah_reward_function, o_handler)
+    want = o_ev(state.double(), actions.double(), 0).numpy()
+    helpers.compare_returns(got, want, max_jump_frac=0.02, **TOL[precision])
+    nxt = ev.predict_next_state(state, actions[0, :, 0]).cpu().numpy()
+    np.testing.assert_allclose(nxt, o_ev.predict_next_state(state.double(), actions[0, :, 0].double()).numpy(), rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_infinite_returns_pass_through(cuda_device, precision):
+    """deterministic.py:75-77 replaces NaN returns only: +inf and -inf reach the optimizer unchanged."""
+    from blackbox_mpc_b200.trajectory_evaluators.deterministic import DeterministicTrajectoryEvaluator
+    from blackbox_mpc_b200.utils import rewards
+    src = """
+    __device__ float reward(const float* s, const float* a, const float* s2) {
+      if (a[0] > 0.9f) return __int_as_float(0x7f800000);        // +inf
+      if (a[0] < -0.9f) return -__int_as_float(0x7f800000);      // -inf
+      return s2[0] - s[0];
+    }"""
+    P = 400
+    w = workloads.make("C3", population_size=P, planning_horizon=6, bias_scale=0.1)
+    policy = workloads.build_policy(w, precision=precision)
+    ev = DeterministicTrajectoryEvaluator(reward_function=rewards.cuda_reward(src),
+                                          system_dynamics_handler=policy._trajectory_evaluator._system_dynamics_handler)
+    actions = helpers.random_actions(w, P, seed=14) * 0.5            # |a| <= 0.5: finite by default
+    actions[3, 0, 2, 0] = 0.95                                       # +inf once
+    actions[5, 0, 4, 0] = -0.95                                      # -inf once
+    actions[7, 0, 1, 0], actions[7, 0, 3, 0] = 0.95, -0.95           # +inf - inf = NaN -> -1e6
+    got = ev(torch.from_numpy(w.state), actions, 0).cpu().numpy()[:, 0]
+    assert got[3] == np.inf and got[5] == -np.inf and got[7] == np.float32(-1e6)
+    assert np.isfinite(np.delete(got, [3, 5, 7])).all()
