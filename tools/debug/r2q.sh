@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+B="python bench.py --steps 20 --warmup 4 --no-cpu-baseline"
+ext() { python -c "import json,sys; d=json.loads([l for l in sys.stdin if l.startswith('{')][0]); print('$1', 'steps/s', round(d['value'],1), 'ms', round(d['ms_per_step'],3), d['roofline']['kernel'], 'kernel_ms', round(d['roofline']['kernel_ms_avg'],4))"; }
+timeout 200 $B 2>> gpurun_out/r2q_err.log | ext "base"
+for X in 2 4 8 12 10 14; do BBMPC_TC_X=$X timeout 200 $B 2>> gpurun_out/r2q_err.log | ext "X=$X"; done
+timeout 200 $B --precision bf16 2>> gpurun_out/r2q_err.log | ext "bf16x1"
+BBMPC_TC_X=14 timeout 200 $B --precision bf16 2>> gpurun_out/r2q_err.log | ext "bf16x1 X=14"
+tail -n 3 gpurun_out/r2q_err.log
