@@ -48,26 +48,15 @@ using namespace tc05;
 #ifndef PIPE_ISSUE_VARIANT
 #define PIPE_ISSUE_VARIANT 0   // how the MMA issuer emits a ring unit (A/B builds, tools/debug/build_variant.sh)
 #endif
-#ifndef PIPE_CONV_PER_Q
-#define PIPE_CONV_PER_Q 2      // conversion warps per TMEM lane quarter (2: 20 warps, 3: 24 warps)
-#endif
-constexpr int PIPE_CQ = PIPE_CONV_PER_Q;
-constexpr int PIPE_WARPS = 12 + 4 * PIPE_CQ;
+constexpr int PIPE_WARPS = 20;
 constexpr int PIPE_THREADS = 32 * PIPE_WARPS;
-constexpr int PIPE_DRAIN_COUNT = 8 * PIPE_CQ;   // D-buffer readers: 4 PIPE_CQ conversion warps x 2, or 4 output readers x 2 PIPE_CQ
 constexpr int PIPE_MAX_MT = 3;          // member-tiles per CTA and round
 constexpr int PIPE_MAX_WSTAGES = 8;
 constexpr int PIPE_MAX_UNITS = 16;      // A-ring positions
 constexpr int PIPE_ROWS = 128;
 // register budgets per warpgroup role.  setmaxnreg moves registers inside the CTA's LAUNCH allocation (640 threads x 96), not the
 // SM's file: the budgets must sum to 5 warpgroups x 96 = 480 (64 + 32 + 144 + 2 x 120), or the last setmaxnreg.inc never returns.
-#if PIPE_CONV_PER_Q == 2
 constexpr int PIPE_REGS_CTRL = 64, PIPE_REGS_PUB = 32, PIPE_REGS_INT = 144, PIPE_REGS_CONV = 120;
-#else   // 768 threads x 80: 6 warpgroups x 80 = 480 = 56 + 24 + 112 + 3 x 96
-constexpr int PIPE_REGS_CTRL = 56, PIPE_REGS_PUB = 24, PIPE_REGS_INT = 112, PIPE_REGS_CONV = 96;
-#endif
-static_assert(PIPE_REGS_CTRL + PIPE_REGS_PUB + PIPE_REGS_INT + PIPE_CQ * PIPE_REGS_CONV == (PIPE_WARPS / 4) * ((65536 / PIPE_THREADS) / 8 * 8),
-              "setmaxnreg budgets must sum to the launch allocation");
 
 struct PipeParams {
   MlpDev mlp;
@@ -85,6 +74,7 @@ struct PipeParams {
   float* traj;                       // user reward: visited states [rows][H][dS] (else nullptr)
   float* park;                       // integrators' parked states: [grid][PIPE_MAX_MT][DS_T/4 + 1][128] float4
   uint32_t* trace; int xflags;
+  int dfull_polls;                   // conversion warps: non-blocking probes of an accumulator barrier before they sleep on it
   int stagger;                       // cycles by which the odd-chunk conversion warps start late (de-phases compute / store)
   uint32_t* dbg;                     // host-mapped watchdog record (BBMPC_DEBUG=1), else nullptr
 };
@@ -154,28 +144,6 @@ __device__ __forceinline__ void pconv_full(const uint32_t (&r)[16], uint32_t (&h
     for (int j = 0; j < 8; ++j) split_bf16x2_veltkamp(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
   }
 }
-// Trailing chunks (real features | ones-columns meeting the bias rows | zero padding): v = act(D) * mask + add.
-template <int ACT>
-__device__ __forceinline__ void pconv_tail(const uint32_t (&r)[16], bool has_data, const float* mk_ad, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
-  float v[16];
-  if (has_data) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-    act16<ACT>(v);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = 0.0f;
-  }
-#pragma unroll
-  for (int j = 0; j < 16; j += 4) {
-    const float4 mk = *reinterpret_cast<const float4*>(mk_ad + j), ad = *reinterpret_cast<const float4*>(mk_ad + 16 + j);
-    v[j] = fmaf(v[j], mk.x, ad.x); v[j + 1] = fmaf(v[j + 1], mk.y, ad.y);
-    v[j + 2] = fmaf(v[j + 2], mk.z, ad.z); v[j + 3] = fmaf(v[j + 3], mk.w, ad.w);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) split_bf16x2_veltkamp(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-}
-
 // One hidden-layer conversion of one warp: chunks c = sub, sub+2, ... of its 32 TMEM lanes.  Measured (ncu source
 // page, profiles/r2*): with two conversion warps per scheduler the loop is bound by the dependent-issue latency of
 // one chunk's tanh + hi/lo split (about 120 instructions, 300 cycles of fixed stalls), not by a pipe.  So a warp
@@ -186,7 +154,7 @@ template <int ACT, bool TR>
 __device__ __forceinline__ void pipe_convert(uint32_t taddr, int Npad, int N, int n_a_chunks, int sub, int passes,
                                             uint32_t aring, uint32_t chunk_bytes, uint32_t a_units, uint32_t pu, uint32_t wrap,
                                             uint32_t bar_afull, uint32_t bar_afree, uint32_t bar_drained, uint32_t bar_adone, int row, int lane,
-                                            const float* tail_tab, int stagger, volatile uint32_t* dbgp, PTracer<TR>& tr) {
+                                            const float* tail_tab, int stagger, uint32_t polls, volatile uint32_t* dbgp, PTracer<TR>& tr) {
   // bar_adone != 0 (two jobs in flight): the MMA issuer waits once for the whole operand instead of per ring unit
   const int n_full = N >> 4;        // chunks whose 16 columns are all real features
   const int n_data = Npad >> 4;     // chunks that carry accumulator data at all
@@ -194,80 +162,76 @@ __device__ __forceinline__ void pipe_convert(uint32_t taddr, int Npad, int N, in
     // The two warps of a quarter share one scheduler and one MUFU pipe: started together they compute together and
     // store together; half a step apart one converts while the other waits for its stores / ring units.
     const long long t0 = clock64();
-    while (clock64() - t0 < stagger * sub * 2 / PIPE_CQ) {}
+    while (clock64() - t0 < stagger) {}
   }
   const uint32_t unit_bytes = 2 * chunk_bytes;
-  const uint32_t free_off = bar_afree - bar_afull;
-  const uint32_t row_off = aring + static_cast<uint32_t>(row) * 16;
-  // chunk c lives in ring unit (pu + c/2) mod a_units, half c & 1; a layer has at most a_units - 1 units: one wrap at most
-  auto locate = [&](int cc, uint32_t& slot, uint32_t& bf, uint32_t& wr) {
-    uint32_t pos = pu + (static_cast<uint32_t>(cc) >> 1);
-    wr = wrap;
-    if (pos >= a_units) { pos -= a_units; ++wr; }
-    slot = row_off + pos * unit_bytes + (static_cast<uint32_t>(cc) & 1u) * chunk_bytes;
-    bf = bar_afull + 8 * pos;
-  };
+  uint32_t slot = aring + pu * unit_bytes + static_cast<uint32_t>(sub) * chunk_bytes + static_cast<uint32_t>(row) * 16;
+  uint32_t bf = bar_afull + 8 * pu;
+  const uint32_t bf_end = bar_afull + 8 * a_units, free_off = bar_afree - bar_afull;
   auto store = [&](const uint32_t (&hi)[8], const uint32_t (&lo)[8], uint32_t at) {
-    if (passes & 16) return;   // timing experiment (BBMPC_TC_X & 8): no operand stores, results garbage
     st_shared_v4(at, hi[0], hi[1], hi[2], hi[3]);
     st_shared_v4(at + PIPE_ROWS * 16, hi[4], hi[5], hi[6], hi[7]);
-    if ((passes & 15) == 3) {
+    if (passes == 3) {
       st_shared_v4(at + 2 * PIPE_ROWS * 16, lo[0], lo[1], lo[2], lo[3]);
       st_shared_v4(at + 3 * PIPE_ROWS * 16, lo[4], lo[5], lo[6], lo[7]);
     }
   };
-  auto arrive = [&](int cc, uint32_t bf) {   // a lone last chunk stands for its missing partner
-    if ((cc ^ 1) < n_a_chunks) mbar_arrive(bf); else mbar_arrive_n(bf, 2);
+  auto advance = [&]() {
+    slot += unit_bytes; bf += 8;
+    if (bf == bf_end) { slot -= a_units * unit_bytes; bf = bar_afull; ++wrap; }
   };
   auto drained = [&]() {   // this warp's last read of the accumulator is complete: the D buffer may be overwritten
     fence_before_sync();
     __syncwarp();
-    if (lane == 0) mbar_arrive_n(bar_drained, 2);
+    if (lane == 0) mbar_arrive(bar_drained);
   };
   int c = sub;
   // ---- pairs of full chunks
-  for (; c + PIPE_CQ < n_full; c += 2 * PIPE_CQ) {
+  for (; c + 2 < n_full; c += 4) {
     tr.rec(0x100u | c);
     uint32_t ra[16], rb[16];
     tmem_ld16(taddr + 16 * c, ra);
-    tmem_ld16(taddr + 16 * (c + PIPE_CQ), rb);
+    tmem_ld16(taddr + 16 * (c + 2), rb);
     // probe the two ring units now (non-blocking); the answers are needed only after the conversion
-    uint32_t slot0, bf0, w0, slot1, bf1, w1;
-    locate(c, slot0, bf0, w0);
-    locate(c + PIPE_CQ, slot1, bf1, w1);
     uint32_t ok0 = 1, ok1 = 1;
-    if (w0 > 0) ok0 = mbar_test_wait(bf0 + free_off, (w0 - 1) & 1u);
-    if (w1 > 0) ok1 = mbar_test_wait(bf1 + free_off, (w1 - 1) & 1u);
+    {
+      uint32_t bf1 = bf + 8, wrap1 = wrap;
+      if (bf1 == bf_end) { bf1 = bar_afull; ++wrap1; }
+      if (wrap > 0) ok0 = mbar_test_wait(bf + free_off, (wrap - 1) & 1u);
+      if (wrap1 > 0) ok1 = mbar_test_wait(bf1 + free_off, (wrap1 - 1) & 1u);
+    }
     wait_ld();
-    if (c + 2 * PIPE_CQ >= n_data) drained();
+    if (c + 4 >= n_data) drained();
     uint32_t hia[8], loa[8], hib[8], lob[8];
     pconv_full<ACT>(ra, hia, loa);
     pconv_full<ACT>(rb, hib, lob);
     tr.rec(0x200u | c);
-    if (!ok0) mbar_wait_sleep(bf0 + free_off, (w0 - 1) & 1u, dbgp, 0x8000000u | (c << 8));
+    if (!ok0) mbar_wait_poll_then_sleep(bf + free_off, (wrap - 1) & 1u, polls, dbgp, 0x8000000u | (c << 8));
+    const uint32_t slot0 = slot, bf0 = bf;
     store(hia, loa, slot0);
-    if (!ok1) mbar_wait_sleep(bf1 + free_off, (w1 - 1) & 1u, dbgp, 0x8100000u | (c << 8));
-    store(hib, lob, slot1);
+    advance();
+    if (!ok1) mbar_wait_poll_then_sleep(bf + free_off, (wrap - 1) & 1u, polls, dbgp, 0x8100000u | (c << 8));
+    store(hib, lob, slot);
     fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
-    arrive(c, bf0);             // (per-unit arrivals in every mode: the barrier phases must stay in step with the ring across rounds)
-    arrive(c + PIPE_CQ, bf1);
+    mbar_arrive(bf0);   // (per-unit arrivals in every mode: the barrier phases must stay in step with the ring across rounds)
+    if (((c + 2) ^ 1) < n_a_chunks) mbar_arrive(bf); else mbar_arrive_n(bf, 2);
+    advance();
     tr.rec(0x300u | c);
   }
-  // ---- remaining chunks one at a time (full chunks left over, then the trailing chunks with ones-columns / padding)
-  for (; c < n_a_chunks; c += PIPE_CQ) {
+  // ---- remaining chunks one at a time (at most one full chunk, then the trailing chunks with ones-columns / padding)
+  for (; c < n_a_chunks; c += 2) {
     tr.rec(0x100u | c);
     uint32_t r[16];
-    if (c < n_data) { tmem_ld16(taddr + 16 * c, r); wait_ld(); if (c + PIPE_CQ >= n_data) drained(); }
+    if (c < n_data) { tmem_ld16(taddr + 16 * c, r); wait_ld(); if (c + 2 >= n_data) drained(); }
     uint32_t hi[8], lo[8];
     if (c < n_full) pconv_full<ACT>(r, hi, lo);
-    else pconv_tail<ACT>(r, c < n_data, tail_tab + 32 * (c - n_full), hi, lo);
+    else tail16<ACT>(r, c < n_data, N - 16 * c, tail_tab + 32 * (c - n_full), hi, lo);
     tr.rec(0x200u | c);
-    uint32_t slot, bf, w;
-    locate(c, slot, bf, w);
-    if (w > 0) mbar_wait_sleep(bf + free_off, (w - 1) & 1u, dbgp, 0x8200000u | (c << 8));
+    if (wrap > 0) mbar_wait_poll_then_sleep(bf + free_off, (wrap - 1) & 1u, polls, dbgp, 0x8200000u | (c << 8));
     store(hi, lo, slot);
     fence_proxy_async_smem();
-    arrive(c, bf);
+    if ((c ^ 1) < n_a_chunks) mbar_arrive(bf); else mbar_arrive_n(bf, 2);   // a lone last chunk stands for its missing partner
+    advance();
     tr.rec(0x300u | c);
   }
   if (sub >= n_data) drained();   // no chunk of this warp carried accumulator data
@@ -293,8 +257,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
   const uint32_t bar_afree = bar_afull + PIPE_MAX_UNITS * 8;       // MMA -> conversion: ring unit consumed (commit)
   const uint32_t bar_dfull = bar_afree + PIPE_MAX_UNITS * 8;       // MMA -> conversion: hidden accumulator in D[b] complete
   const uint32_t bar_dout = bar_dfull + 16;                        // MMA -> publishers / integrators: output accumulator in D[b]
-  const uint32_t bar_drained = bar_dout + 16;                      // readers -> MMA: D[b] has been read (PIPE_DRAIN_COUNT arrivals)
-  const uint32_t bar_adone = bar_drained + 16;                     // conversion -> MMA (two jobs in flight): the whole A operand of slot b is in the ring (one arrival per conversion warp)
+  const uint32_t bar_drained = bar_dout + 16;                      // readers -> MMA: D[b] has been read (8 arrivals)
+  const uint32_t bar_adone = bar_drained + 16;                     // conversion -> MMA (two jobs in flight): the whole A operand of slot b is in the ring (8 arrivals)
   const uint32_t bar_xfull = bar_adone + 16;                       // integrators -> MMA: X region i written (4 arrivals)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + lay.tmem_slot);
   float* st_mean_t = reinterpret_cast<float*>(smem + lay.stats);
@@ -329,8 +293,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
   if (tid == 0) {
     for (int s = 0; s < p.n_wstages; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
     for (int u = 0; u < p.a_units; ++u) { mbar_init(bar_afull + 8 * u, 256); mbar_init(bar_afree + 8 * u, 1); }   // 2 chunks x 4 quarters x 32 lanes
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_dfull + 8 * b, 1); mbar_init(bar_dout + 8 * b, 1); mbar_init(bar_drained + 8 * b, PIPE_DRAIN_COUNT); }
-    for (int b = 0; b < 2; ++b) mbar_init(bar_adone + 8 * b, 4 * PIPE_CQ);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_dfull + 8 * b, 1); mbar_init(bar_dout + 8 * b, 1); mbar_init(bar_drained + 8 * b, 8); }
+    for (int b = 0; b < 2; ++b) mbar_init(bar_adone + 8 * b, 8);
     for (int i = 0; i < PIPE_MAX_MT; ++i) mbar_init(bar_xfull + 8 * i, 4);
     fence_mbar_init();
     int* cv = reinterpret_cast<int*>(smem + lay.conv);
@@ -387,11 +351,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
           for (int g = g0; g < g1; ++g) {
             const uint2 e = table[g];
             mbar_wait_sleep(bar_wempty + 8 * stage, phase ^ 1, dbgp, 0x6000000u);
-            if ((p.xflags & 4) && phase) { mbar_arrive(bar_wfull + 8 * stage); }   // timing experiment: weights of the first ring fill only
-            else {
-              mbar_arrive_expect_tx(bar_wfull + 8 * stage, e.y);
-              bulk_g2s(smem_base + lay.wring + stage * p.stage_bytes, wimg + e.x, e.y, bar_wfull + 8 * stage);
-            }
+            mbar_arrive_expect_tx(bar_wfull + 8 * stage, e.y);
+            bulk_g2s(smem_base + lay.wring + stage * p.stage_bytes, wimg + e.x, e.y, bar_wfull + 8 * stage);
             if (++stage == static_cast<uint32_t>(p.n_wstages)) { stage = 0; phase ^= 1; }
           }
         }
@@ -556,7 +517,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
           const int i = j % n_mt, t = j / n_mt;
           tr.arm(p.trace && blockIdx.x == 0 && lane == 0 && t == 2);
           const int b = (n_mt == 1) ? b_single : (j & 1);
-          mbar_wait_sleep(bar_dout + 8 * b, (b ? oc1 : oc0) & 1u, dbgp, 0x5000000u | j);
+          mbar_wait_poll_then_sleep(bar_dout + 8 * b, (b ? oc1 : oc0) & 1u, p.dfull_polls, dbgp, 0x5000000u | j);
           if (b) ++oc1; else ++oc0;
           fence_after_sync();
           tr.rec(0x30u);
@@ -567,7 +528,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
           wait_ld();
           fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive_n(bar_drained + 8 * b, 2 * PIPE_CQ);
+          if (lane == 0) mbar_arrive_n(bar_drained + 8 * b, 2);
           const int xi = mt_tile(r, i) % p.xchg_tiles;
           float* base = p.xchg + ((static_cast<size_t>(xi) * 2 + (t & 1)) * nM + mt_member(i)) * (DS_T * PIPE_ROWS);
           float4* mine = reinterpret_cast<float4*>(base + static_cast<size_t>(row_in_tile) * DS_T);
@@ -733,7 +694,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
           fence_after_sync();
         } else {
           const int b = (n_mt == 1) ? b_single : (j & 1);
-          mbar_wait_sleep(bar_dout + 8 * b, (b ? oc1 : oc0) & 1u, dbgp, 0x5000000u | j);
+          mbar_wait_poll_then_sleep(bar_dout + 8 * b, (b ? oc1 : oc0) & 1u, p.dfull_polls, dbgp, 0x5000000u | j);
           if (b) ++oc1; else ++oc0;
           fence_after_sync();
           tr.rec(0x41u);
@@ -744,7 +705,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
           wait_ld();
           fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive_n(bar_drained + 8 * b, 2 * PIPE_CQ);
+          if (lane == 0) mbar_arrive_n(bar_drained + 8 * b, 2);
           const int oact = M.layer[nL - 1].act;
 #pragma unroll
           for (int k = 0; k < DS_T; ++k) {
@@ -813,7 +774,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
     // ============================================================ conversion warps
     const int e = warp - 12;
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch (hardware: warp id % 4)
-    const int sub = e >> 2;                 // chunks sub, sub + PIPE_CQ, ... of the quarter
+    const int sub = e >> 2;                 // 0 / 1: even / odd K-chunks
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const int row_in_tile = q * 32 + lane;
     const int* cv = reinterpret_cast<const int*>(smem + lay.conv);
@@ -832,13 +793,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
         const int n_a_chunks = cv[8 * l + 3];
         const float* tail_tab = reinterpret_cast<const float*>(smem + lay.conv + MAX_LAYERS * 32) + 64 * l;
         const uint32_t taddr = tmem_base + lane_off + (b ? p.col_d1 : p.col_d0);
-        mbar_wait_sleep(bar_dfull + 8 * b, (b ? hc1 : hc0) & 1u, dbgp, 0x4000000u | (j << 8) | l);
+        mbar_wait_poll_then_sleep(bar_dfull + 8 * b, (b ? hc1 : hc0) & 1u, p.dfull_polls, dbgp, 0x4000000u | (j << 8) | l);
         if (b) ++hc1; else ++hc0;
         fence_after_sync();
         tr.rec(0x20u | (l << 8) | (b << 12));
         const uint32_t aring = smem_base + lay.aring;
-#define PIPE_CONV(ACT) pipe_convert<ACT, TR>(taddr, Npad, N, n_a_chunks, sub, p.passes | ((p.xflags & 8) ? 16 : 0), aring, p.a_chunk_bytes, p.a_units, pu, wrap, \
-                                            bar_afull, bar_afree, bar_drained + 8 * b, (seq.single || !(p.xflags & 32)) ? 0u : bar_adone + 8 * b, row_in_tile, lane, tail_tab, p.stagger, dbgp, tr)
+#define PIPE_CONV(ACT) pipe_convert<ACT, TR>(taddr, Npad, N, n_a_chunks, sub, p.passes, aring, p.a_chunk_bytes, p.a_units, pu, wrap, \
+                                            bar_afull, bar_afree, bar_drained + 8 * b, (seq.single || !(p.xflags & 32)) ? 0u : bar_adone + 8 * b, row_in_tile, lane, tail_tab, p.stagger, p.dfull_polls, dbgp, tr)
         if (ACT_T >= 0) {
           PIPE_CONV((ACT_T >= 0 ? ACT_T : 0));
         } else {
@@ -957,7 +918,9 @@ int launch_rollout_pipe(bbmpc_ctx* ctx, const float* states, const float* action
   p.n_tiles = (rows + PIPE_ROWS - 1) / PIPE_ROWS;
   p.jobs = m.mlp.solo_jobs; p.table = m.mlp.solo_table;
   if (const char* x = getenv("BBMPC_TC_X")) p.xflags = atoi(x);
-  p.stagger = 700;
+  p.stagger = 0;
+  p.dfull_polls = 0;    // measured: 0 -> 1.315, 128 -> 1.330, 1024 -> 1.346 ms per C4 rollout (polling warps take issue slots from the converting ones)
+  if (const char* x = getenv("BBMPC_PIPE_DFULL_POLLS")) p.dfull_polls = atoi(x);
   if (const char* x = getenv("BBMPC_PIPE_STAGGER")) p.stagger = atoi(x);
   if (const char* x = getenv("BBMPC_PIPE_MT")) { const int v = atoi(x); if (v >= 1 && v < p.max_mt) p.max_mt = v; }
   if (getenv("BBMPC_TC_TRACE")) {

@@ -148,26 +148,12 @@ __device__ __forceinline__ void convert_full(uint32_t taddr, int c, const uint32
 // bias rows of the next layer's weights, and zero padding: v = act(D) * mask + add with per-column
 // mask / add vectors prepared in shared memory (no per-column tests in the instruction stream).
 template <int ACT>
-__device__ __forceinline__ void convert_tail(uint32_t taddr, int c, bool has_data, const float* mk_ad, int passes) {
-  float v[16];
-  if (has_data) {
-    uint32_t r[16];
-    tmem_ld16(taddr + 16 * c, r);
-    wait_ld();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-    act16<ACT>(v);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = 0.0f;
-  }
-#pragma unroll
-  for (int j = 0; j < 16; j += 4) {
-    const float4 mk = *reinterpret_cast<const float4*>(mk_ad + j), ad = *reinterpret_cast<const float4*>(mk_ad + 16 + j);
-    v[j] = fmaf(v[j], mk.x, ad.x); v[j + 1] = fmaf(v[j + 1], mk.y, ad.y);
-    v[j + 2] = fmaf(v[j + 2], mk.z, ad.z); v[j + 3] = fmaf(v[j + 3], mk.w, ad.w);
-  }
-  store_split(taddr, c, v, passes);
+__device__ __forceinline__ void convert_tail(uint32_t taddr, int c, bool has_data, int n_real, const float* mk_ad, int passes) {
+  uint32_t r[16], hi[8], lo[8];
+  if (has_data) { tmem_ld16(taddr + 16 * c, r); wait_ld(); }
+  tail16<ACT>(r, has_data, n_real, mk_ad, hi, lo);   // tc_epi.cuh (shared with rollout_pipe.cu: identical arithmetic)
+  if (passes == 3) tmem_st16(taddr + 16 * c, hi, lo);
+  else tmem_st8(taddr + 16 * c, hi);
 }
 
 // One hidden-layer epilogue of one warp: 16-column chunks c = sub, sub+EPI_SUB, ... of its TMEM
@@ -194,7 +180,7 @@ __device__ __forceinline__ void epi_hidden(uint32_t taddr, int Npad, int N, int 
       wait_ld();
       convert_full<ACT>(taddr, c, r, passes);
     } else {
-      convert_tail<ACT>(taddr, c, 16 * c < Npad, tail_tab + 32 * (c - n_full), passes);
+      convert_tail<ACT>(taddr, c, 16 * c < Npad, N - 16 * c, tail_tab + 32 * (c - n_full), passes);
     }
     tr.rec(0x300u | c);
     wait_st();

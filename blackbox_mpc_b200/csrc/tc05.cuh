@@ -314,6 +314,9 @@ __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t r; a
 __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
+#ifndef BBMPC_LO_CVT
+#define BBMPC_LO_CVT 1   // 0: integer-pipe rounding (measured slower: 1.416 vs 1.375 ms per C4 rollout together with the FMA-pipe reciprocal)
+#endif
 // Veltkamp hi/lo bf16 split of a packed pair (see split_bf16x2_veltkamp): 4 packed ops + prmt + one cvt.
 // Written as z = 2^16 y (exact), s = fl(y + z), hi = s - z (exact): ptxas contracts mul.rn.f32x2 + sub.rn.f32x2
 // into FFMA2 (it does not for the scalar .rn forms); in the textbook form c = 65537 y, hi = c - (c - y) that
@@ -325,7 +328,14 @@ __device__ __forceinline__ void split_bf16x2_packed(uint64_t y, uint32_t& hi, ui
   float h0, h1, l0, l1;
   upk2(h, h0, h1); upk2(l, l0, l1);
   asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(hi) : "r"(__float_as_uint(h0)), "r"(__float_as_uint(h1)));
+#if BBMPC_LO_CVT
   lo = pack_bf16x2(l0, l1);
+#else
+  // bf16 rounding of the residual on the integer pipe (round half away from zero: +0x8000 on the magnitude bits, keep
+  // the high half): cvt.rn.bf16x2 runs on the MUFU pipe, which bounds the conversion warps (8 of 28 MUFU-pipe
+  // operations per 16-column chunk).  Differs from round-to-nearest-even only on exact ties of the residual.
+  asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(lo) : "r"(__float_as_uint(l0) + 0x8000u), "r"(__float_as_uint(l1) + 0x8000u));
+#endif
 }
 
 }  // namespace tc05
