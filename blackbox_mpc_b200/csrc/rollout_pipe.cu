@@ -459,9 +459,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
                 // one asm block: probes of the next group's weight stage and (single mode) the next ring unit first, the
                 // unit's MMAs and commits by one elected lane, the probe results last (their latency overlaps the issue)
                 uint32_t pw = 0, pa = 0;
-                mma_unit_ss_probe(d, a0, b0, a_lo_off16, job.lo_off16, achunk16, job.chunk16, job.idesc, acc, three ? 1u : 0u, two ? 1u : 0u,
-                                  bar_afree + 8 * pu, last_of_group ? bar_wempty + 8 * stage : 0u,
-                                  bar_wfull + 8 * nstage, nphase, bar_afull + 8 * pn, wn & 1u, pw, pa);
+                if (three && two)   // the common case: a slimmer instruction stream (the issuing warp paces the whole CTA)
+                  mma_unit_ss_probe_full(d, alo, blo, DESC_HI, a_lo_off16, job.lo_off16, achunk16, job.chunk16, job.idesc, acc,
+                                         bar_afree + 8 * pu, last_of_group ? bar_wempty + 8 * stage : 0u,
+                                         bar_wfull + 8 * nstage, nphase, bar_afull + 8 * pn, wn & 1u, pw, pa);
+                else
+                  mma_unit_ss_probe(d, a0, b0, a_lo_off16, job.lo_off16, achunk16, job.chunk16, job.idesc, acc, three ? 1u : 0u, two ? 1u : 0u,
+                                    bar_afree + 8 * pu, last_of_group ? bar_wempty + 8 * stage : 0u,
+                                    bar_wfull + 8 * nstage, nphase, bar_afull + 8 * pn, wn & 1u, pw, pa);
                 ok_w = (last_of_group && g + 1 < job.ngroups) ? pw : 0u;
                 ok_a = (!whole && u + 1 < n_units) ? pa : 0u;
 #else

@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+B="python bench.py --steps 30 --warmup 5 --no-cpu-baseline"
+ext() { python -c "import json,sys; d=json.loads([l for l in sys.stdin if l.startswith('{')][0]); print('$1', 'steps/s', round(d['value'],1), 'ms', round(d['ms_per_step'],3), d['roofline']['kernel'], 'kernel_ms', round(d['roofline']['kernel_ms_avg'],4), 'frac', round(d['roofline']['frac'],4))"; }
+timeout 300 python -m pytest tests/test_gpu_pipe.py -x -q 2>&1 | tail -2
+timeout 200 $B 2>> gpurun_out/r2x_err.log | ext "C4"
+timeout 200 $B --population 5000 2>> gpurun_out/r2x_err.log | ext "C4 P5000"
+timeout 200 $B --workload C5 2>> gpurun_out/r2x_err.log | ext "C5"
+tail -n 3 gpurun_out/r2x_err.log
