@@ -12,8 +12,11 @@
 //                (the SVD of a symmetric PSD matrix, :195-198) with cuSOLVER syevd, loaded lazily.
 // sigma is a per-coordinate VECTOR as in the reference (:97); D is kept as its diagonal.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <mutex>
+#include <string>
 #include "common.cuh"
 #include "device_fns.cuh"
 #include "refit.cuh"
@@ -26,31 +29,35 @@ namespace {
 enum { K_MUEFF = 0, K_CSIGMA, K_DSIGMA, K_CC, K_C1, K_CMU, K_EN, K_N };
 
 // ---- lazily bound cuSOLVER (only CMA-ES needs it; libbbmpc.so itself does not link it)
+// The dlopen'ed function table is process-wide (bound once); the cuSOLVER handle, its workspace and devInfo belong to the
+// optimizer handle (bbmpc_opt::eig_*): one per device / stream user, freed with the handle.
 struct Solver {
   void* lib = nullptr;
-  void* handle = nullptr;
+  bool ok = false; std::string err;
   int (*create)(void**) = nullptr;
   int (*destroy)(void*) = nullptr;
   int (*set_stream)(void*, cudaStream_t) = nullptr;
   int (*buffer_size)(void*, int, int, int, const float*, int, const float*, int*) = nullptr;
   int (*syevd)(void*, int, int, int, float*, int, float*, float*, int, int*) = nullptr;
-  float* work = nullptr; int lwork = 0; int* info = nullptr;
 };
 Solver g_solver;
+std::once_flag g_solver_once;
 
 int solver_init(bbmpc_ctx* ctx) {
   Solver& s = g_solver;
-  if (s.handle) return BBMPC_OK;
-  const char* names[] = {"libcusolver.so.11", "libcusolver.so", "/usr/local/cuda/lib64/libcusolver.so.11", "libcusolver.so.12"};
-  for (const char* n : names) { s.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (s.lib) break; }
-  if (!s.lib) return fail(ctx, BBMPC_ECUDA, "CMA-ES needs libcusolver (dlopen failed: %s)", dlerror());
-  s.create = reinterpret_cast<decltype(s.create)>(dlsym(s.lib, "cusolverDnCreate"));
-  s.destroy = reinterpret_cast<decltype(s.destroy)>(dlsym(s.lib, "cusolverDnDestroy"));
-  s.set_stream = reinterpret_cast<decltype(s.set_stream)>(dlsym(s.lib, "cusolverDnSetStream"));
-  s.buffer_size = reinterpret_cast<decltype(s.buffer_size)>(dlsym(s.lib, "cusolverDnSsyevd_bufferSize"));
-  s.syevd = reinterpret_cast<decltype(s.syevd)>(dlsym(s.lib, "cusolverDnSsyevd"));
-  if (!s.create || !s.set_stream || !s.buffer_size || !s.syevd) return fail(ctx, BBMPC_ECUDA, "libcusolver lacks cusolverDnSsyevd");
-  if (s.create(&s.handle) != 0) { s.handle = nullptr; return fail(ctx, BBMPC_ECUDA, "cusolverDnCreate failed"); }
+  std::call_once(g_solver_once, [&s] {
+    const char* names[] = {"libcusolver.so.11", "libcusolver.so", "/usr/local/cuda/lib64/libcusolver.so.11", "libcusolver.so.12"};
+    for (const char* n : names) { s.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (s.lib) break; }
+    if (!s.lib) { s.err = std::string("CMA-ES needs libcusolver (dlopen failed: ") + dlerror() + ")"; return; }
+    s.create = reinterpret_cast<decltype(s.create)>(dlsym(s.lib, "cusolverDnCreate"));
+    s.destroy = reinterpret_cast<decltype(s.destroy)>(dlsym(s.lib, "cusolverDnDestroy"));
+    s.set_stream = reinterpret_cast<decltype(s.set_stream)>(dlsym(s.lib, "cusolverDnSetStream"));
+    s.buffer_size = reinterpret_cast<decltype(s.buffer_size)>(dlsym(s.lib, "cusolverDnSsyevd_bufferSize"));
+    s.syevd = reinterpret_cast<decltype(s.syevd)>(dlsym(s.lib, "cusolverDnSsyevd"));
+    if (!s.create || !s.destroy || !s.set_stream || !s.buffer_size || !s.syevd) { s.err = "libcusolver lacks cusolverDnSsyevd"; return; }
+    s.ok = true;
+  });
+  if (!s.ok) return fail(ctx, BBMPC_ECUDA, "%s", s.err.c_str());
   return BBMPC_OK;
 }
 
@@ -303,19 +310,21 @@ int cmaes_create(bbmpc_opt* o) {
   ctx->launches += 3;
   // eigensolver workspace
   Solver& s = g_solver;
+  if (s.create(&o->eig_handle) != 0) { o->eig_handle = nullptr; return fail(ctx, BBMPC_ECUDA, "cusolverDnCreate failed"); }
   int lwork = 0;
-  if (s.buffer_size(s.handle, 1 /*CUSOLVER_EIG_MODE_VECTOR*/, 0 /*CUBLAS_FILL_MODE_LOWER*/, N, o->d_z, N, o->d_z + NN, &lwork) != 0)
+  if (s.buffer_size(o->eig_handle, 1 /*CUSOLVER_EIG_MODE_VECTOR*/, 0 /*CUBLAS_FILL_MODE_LOWER*/, N, o->d_z, N, o->d_z + NN, &lwork) != 0)
     return fail(ctx, BBMPC_ECUDA, "cusolverDnSsyevd_bufferSize failed");
-  if (lwork > s.lwork) {
-    cudaFree(s.work);
-    if (cudaMalloc(&s.work, static_cast<size_t>(lwork) * sizeof(float)) != cudaSuccess) return fail(ctx, BBMPC_ENOMEM, "eigensolver workspace");
-    s.lwork = lwork;
-  }
-  if (!s.info && cudaMalloc(&s.info, sizeof(int)) != cudaSuccess) return fail(ctx, BBMPC_ENOMEM, "eigensolver info");
+  if (cudaMalloc(&o->eig_work, static_cast<size_t>(lwork) * sizeof(float)) != cudaSuccess) return fail(ctx, BBMPC_ENOMEM, "eigensolver workspace");
+  o->eig_lwork = lwork;
+  if (cudaMalloc(&o->eig_info, sizeof(int)) != cudaSuccess) return fail(ctx, BBMPC_ENOMEM, "eigensolver info");
   return BBMPC_OK;
 }
 
-void cmaes_destroy(bbmpc_opt*) {}
+void cmaes_destroy(bbmpc_opt* o) {
+  if (o->eig_handle) g_solver.destroy(o->eig_handle);
+  cudaFree(o->eig_work); cudaFree(o->eig_info);
+  o->eig_handle = nullptr; o->eig_work = nullptr; o->eig_info = nullptr; o->eig_lwork = 0;
+}
 
 int cmaes_set_shard(bbmpc_opt* o) {
   // excess^2 scratch [P_local*A, HU] and the per-population reward sums live in d_work / d_penalty-sized buffers
@@ -380,9 +389,15 @@ int cmaes_iter_merge(bbmpc_opt* o, int /*iter*/, const float* partials, int worl
   cmaes_cov_kernel<<<grd, blk, 0, st>>>(a); BB_LAUNCH_CHECK(ctx);
   BB_CUDA(ctx, cudaMemcpyAsync(eigm, o->d_C, NN * sizeof(float), cudaMemcpyDeviceToDevice, st));
   Solver& s = g_solver;
-  if (s.set_stream(s.handle, st) != 0) return fail(ctx, BBMPC_ECUDA, "cusolverDnSetStream failed");
-  if (s.syevd(s.handle, 1, 0, N, eigm, N, eigw, s.work, s.lwork, s.info) != 0) return fail(ctx, BBMPC_ECUDA, "cusolverDnSsyevd failed");
+  if (s.set_stream(o->eig_handle, st) != 0) return fail(ctx, BBMPC_ECUDA, "cusolverDnSetStream failed");
+  if (s.syevd(o->eig_handle, 1, 0, N, eigm, N, eigw, o->eig_work, o->eig_lwork, o->eig_info) != 0) return fail(ctx, BBMPC_ECUDA, "cusolverDnSsyevd failed");
   ctx->launches++;
+  if (getenv("BBMPC_DEBUG")) {   // BBMPC_DEBUG=1: devInfo of the eigensolve (costs a synchronisation per iteration)
+    int info = 0;
+    BB_CUDA(ctx, cudaMemcpyAsync(&info, o->eig_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (info != 0) return fail(ctx, BBMPC_ECUDA, "cusolverDnSsyevd: devInfo = %d (eigensolve of the CMA-ES covariance did not converge)", info);
+  }
   eig_finish_kernel<<<grid_for(NN, 256), 256, 0, st>>>(eigm, eigw, o->d_B, o->d_D, N); BB_LAUNCH_CHECK(ctx);
   return BBMPC_OK;
 }

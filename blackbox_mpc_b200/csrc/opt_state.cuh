@@ -36,6 +36,8 @@ struct bbmpc_opt {
   float *d_m = nullptr, *d_sigma = nullptr, *d_C = nullptr, *d_B = nullptr, *d_D = nullptr, *d_ps = nullptr,
         *d_pc = nullptr, *d_z = nullptr, *d_BD = nullptr, *d_work = nullptr, *d_cma_w = nullptr;
   double cma_consts[16] = {0};
+  // CMA-ES eigensolver state of THIS handle (cuSOLVER handle on the context's device, workspace, devInfo)
+  void* eig_handle = nullptr; float* eig_work = nullptr; int eig_lwork = 0; int* eig_info = nullptr;
   // peer-memory exchange: [2 parities][partial_floats] messages + one sequence flag (last 64 bytes)
   float* p2p_buf = nullptr; size_t p2p_bytes = 0;
   float** d_peer = nullptr;        // [world] device table of the ranks' exchange buffers (own entry = p2p_buf)

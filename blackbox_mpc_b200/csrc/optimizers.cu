@@ -647,6 +647,7 @@ void bbmpc_opt_destroy(bbmpc_opt* o) {
   cudaDeviceSynchronize();
   if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
   if (o->graph_stream) cudaStreamDestroy(o->graph_stream);
+  if (o->cfg.kind == BBMPC_OPT_CMAES) cmaes_destroy(o);
   for (void* p : o->p2p_opened) cudaIpcCloseMemHandle(p);
   for (void* p : o->owned) cudaFree(p);
   if (o->h_pinned) cudaFreeHost(o->h_pinned);
