@@ -419,6 +419,47 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
           // Readiness of the CURRENT unit's weight stage / ring unit, learnt from the probe issued with the previous unit
           // (ok_w only matters at the first unit of a group, ok_a at every unit of a layer >= 1 in single mode).
           uint32_t ok_w = 0, ok_a = 0;
+#if PIPE_ISSUE_VARIANT == 0
+          if (l > 0 && three && !whole) {
+            // Layers >= 1: flat loop over the ring units, addresses advance by constants (the issuing warp shares its
+            // scheduler with two conversion warps: every instruction of this loop is paid ~10 cycles).  A weight group
+            // (ring stage) holds n >= 1 units: wide layers one, the output layer several.
+            uint32_t alo = a_desc_lo_base | ((aring16 + 2 * pu * achunk16) & 0x3FFFu);
+            const uint32_t alo0 = a_desc_lo_base | (aring16 & 0x3FFFu), astep = 2 * achunk16, bstep = 2 * job.chunk16;
+            uint32_t gsz = job.gsz, n = gsz & 15u, kk = 0;
+            uint32_t blo = job.desc_lo_base | ((wring16 + stage * stage16) & 0x3FFFu);
+            for (; u < n_units; ++u) {
+              if (kk == 0 && !ok_w) mbar_wait(bar_wfull + 8 * stage, phase, dbgp, 0x3000000u | (l << 8) | u);
+              if (!ok_a) mbar_wait_poll(bar_afull + 8 * pu, wrap & 1u, dbgp, 0x2000000u | (j << 12) | (l << 8) | u);
+              fence_after_sync();
+              tr.rec(0x4200u | u);
+              const bool last = (kk + 1 == n), more = u + 1 < n_units;
+              uint32_t nstage = stage + 1, nphase = phase, pn = pu + 1, wn = wrap;
+              if (nstage == static_cast<uint32_t>(p.n_wstages)) { nstage = 0; nphase ^= 1; }
+              if (pn == static_cast<uint32_t>(p.a_units)) { pn = 0; ++wn; }
+              uint32_t pw = 0, pa = 0;
+              if (2 * u + 1 < job.nchunks)
+                mma_unit_ss_probe_full(d, alo, blo, DESC_HI, a_lo_off16, job.lo_off16, achunk16, job.chunk16, job.idesc, acc,
+                                       bar_afree + 8 * pu, last ? bar_wempty + 8 * stage : 0u, bar_wfull + 8 * nstage, nphase,
+                                       bar_afull + 8 * pn, wn & 1u, pw, pa);
+              else
+                mma_unit_ss_probe(d, (static_cast<uint64_t>(DESC_HI) << 32) | alo, (static_cast<uint64_t>(DESC_HI) << 32) | blo, a_lo_off16,
+                                  job.lo_off16, achunk16, job.chunk16, job.idesc, acc, 1u, 0u, bar_afree + 8 * pu,
+                                  last ? bar_wempty + 8 * stage : 0u, bar_wfull + 8 * nstage, nphase, bar_afull + 8 * pn, wn & 1u, pw, pa);
+              ok_a = more ? pa : 0u;
+              alo = pn ? alo + astep : alo0;
+              pu = pn; wrap = wn; acc = 1u;
+              if (last) {
+                ok_w = more ? pw : 0u;
+                stage = nstage; phase = nphase;
+                gsz >>= 4; n = gsz & 15u; kk = 0;
+                blo = job.desc_lo_base | ((wring16 + stage * stage16) & 0x3FFFu);
+              } else {
+                ++kk; blo += bstep;
+              }
+            }
+          } else
+#endif
           for (uint32_t g = 0; g < job.ngroups; ++g) {
             const uint32_t n = (job.gsz >> (4 * g)) & 15u;
             tr.rec(0x4000u | g);

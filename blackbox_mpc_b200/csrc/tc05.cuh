@@ -373,8 +373,11 @@ __device__ __forceinline__ void split_bf16x2_packed(uint64_t y, uint32_t& hi, ui
   float h0, h1, l0, l1;
   upk2(h, h0, h1); upk2(l, l0, l1);
   asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(hi) : "r"(__float_as_uint(h0)), "r"(__float_as_uint(h1)));
-#if BBMPC_LO_CVT
+#if BBMPC_LO_CVT == 1
   lo = pack_bf16x2(l0, l1);
+#elif BBMPC_LO_CVT == 2
+  // residual TRUNCATED to bf16 (one PRMT, no MUFU-pipe cvt): |y - hi - lo| <= 2^-8 |lo| <= 2^-17 |y| instead of 2^-18
+  asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(lo) : "r"(__float_as_uint(l0)), "r"(__float_as_uint(l1)));
 #else
   // bf16 rounding of the residual on the integer pipe (round half away from zero: +0x8000 on the magnitude bits, keep
   // the high half): cvt.rn.bf16x2 runs on the MUFU pipe, which bounds the conversion warps (8 of 28 MUFU-pipe
