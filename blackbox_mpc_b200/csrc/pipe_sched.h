@@ -25,17 +25,22 @@
 namespace bbmpc {
 
 struct StageSeq {
-  int nL, single, merged;
+  int nL, single, merged, nmt;
   // per slot: next stage index / number of stages (stage e: job = slot + 2 * (e / nL), layer = e % nL); scalars, not
-  // arrays, so that the device code keeps them in registers
+  // arrays, so that the device code keeps them in registers.  q / r / t: e / nL, e % nL and (job % n_mt) of the slot's
+  // current job, carried along instead of divided out (the walkers are latency-critical single warps).
   int e0, e1, n0, n1;
+  int q0, q1, r0, r1, t0, t1;
   int turn, lead, grp_left, cur;
 
   PIPE_HD void init(int n_jobs, int n_layers, int n_mt) {
     nL = n_layers;
+    nmt = n_mt;
     single = (n_mt == 1);
     merged = (n_mt >= 3 && n_layers >= 2);
     e0 = e1 = 0;
+    q0 = q1 = r0 = r1 = 0;
+    t0 = 0; t1 = (n_mt > 1) ? 1 : 0;
     if (single) { n0 = nL * n_jobs; n1 = 0; }
     else { n0 = nL * ((n_jobs + 1) / 2); n1 = nL * (n_jobs / 2); }
     // slot 0 runs `lead` groups before slot 1 starts (about half a job: the jobs then start and finish in job order
@@ -46,12 +51,14 @@ struct StageSeq {
     cur = 0;
   }
 
-  // Next stage in issue order: job j, layer l, accumulator buffer b.  false when the round is complete.
-  PIPE_HD bool next(int& j, int& l, int& b) {
+  // Next stage in issue order: job j, layer l, accumulator buffer b, member-tile slot i = j % n_mt of the CTA.
+  // false when the round is complete.
+  PIPE_HD bool next(int& j, int& l, int& b, int& i) {
     if (single) {
       if (e0 >= n0) return false;
-      j = e0 / nL; l = e0 - j * nL; b = l & 1;
+      j = q0; l = r0; b = l & 1; i = 0;
       ++e0;
+      if (++r0 == nL) { r0 = 0; ++q0; }
       return true;
     }
     if (grp_left == 0) {
@@ -61,16 +68,23 @@ struct StageSeq {
       const int es = s ? e1 : e0, ns = s ? n1 : n0;
       if (es >= ns) return false;
       cur = s;
-      grp_left = (merged && es % nL == nL - 1 && es + 1 < ns) ? 2 : 1;
+      grp_left = (merged && (s ? r1 : r0) == nL - 1 && es + 1 < ns) ? 2 : 1;
     }
     const int s = cur;
-    const int es = s ? e1 : e0;
-    const int q = es / nL;
-    j = s + 2 * q; l = es - q * nL; b = s;
-    if (s) ++e1; else ++e0;
+    b = s;
+    if (s) {
+      j = 1 + 2 * q1; l = r1; i = t1;
+      ++e1;
+      if (++r1 == nL) { r1 = 0; ++q1; t1 += 2; if (t1 >= nmt) t1 -= nmt; }
+    } else {
+      j = 2 * q0; l = r0; i = t0;
+      ++e0;
+      if (++r0 == nL) { r0 = 0; ++q0; t0 += 2; if (t0 >= nmt) t0 -= nmt; }
+    }
     --grp_left;
     return true;
   }
+  PIPE_HD bool next(int& j, int& l, int& b) { int i; return next(j, l, b, i); }
 };
 
 }  // namespace bbmpc

@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
       // measured ~200 cycles per MMA instead of ~50, profiles/r2*.)
       const bool three = (p.passes == 3);
       uint32_t stage = 0, phase = 0;
-      uint32_t useq = 0;                    // ring units allocated so far (mirrors the conversion warps)
+      uint32_t upos = 0, uwrap = 0;         // ring position / wrap count of the next unit to allocate (mirrors the conversion warps)
       uint32_t dw0 = 0, dw1 = 0;            // stages issued into D[0] / D[1]
       uint32_t xc0 = 0, xc1 = 0, xc2 = 0;   // layer-0 inputs consumed per X region (barrier phases persist across rounds)
       uint32_t ad0 = 0, ad1 = 0;            // whole-operand completions consumed per slot (two jobs in flight)
@@ -378,12 +378,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
       for (int r = 0; r < n_rounds; ++r) {
         const int n_mt = round_count(r);
         if (n_mt == 0) continue;
-        uint32_t ab0 = 0, ab1 = 0;            // first ring unit of the pending A operand (per slot; ab0 in single mode)
+        uint32_t ab0p = 0, ab0w = 0, ab1p = 0, ab1w = 0;   // first ring unit (position, wrap) of the pending A operand per slot (slot 0 in single mode)
         StageSeq seq; seq.init(n_mt * p.H, nL, n_mt);
         int j, l, b;
-        while (seq.next(j, l, b)) {
-          const int i = j % n_mt;
-          tr.arm(p.trace && blockIdx.x == 0 && lane == 0 && j / n_mt == 2);
+        int i;
+        while (seq.next(j, l, b, i)) {
+          if (TR) tr.arm(p.trace && blockIdx.x == 0 && lane == 0 && j / n_mt == 2);
           const TcJob job = jobs[l];
           const uint32_t d = tmem_base + (b ? p.col_d1 : p.col_d0);
           {
@@ -397,12 +397,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
             if (i == 0) ++xc0; else if (i == 1) ++xc1; else ++xc2;
           }
           const bool key1 = !seq.single && b;
-          const uint32_t ub = key1 ? ab1 : ab0;
-          if (l + 1 < nL) {
-            if (key1) ab1 = useq; else ab0 = useq;
-            useq += (static_cast<uint32_t>(jobs[l + 1].nchunks) + 1u) >> 1;
+          uint32_t pu = key1 ? ab1p : ab0p, wrap = key1 ? ab1w : ab0w;   // first ring unit of this stage's A operand
+          if (l + 1 < nL) {   // ring units of the operand the conversion warps will produce from this stage's accumulator
+            if (key1) { ab1p = upos; ab1w = uwrap; } else { ab0p = upos; ab0w = uwrap; }
+            upos += (static_cast<uint32_t>(jobs[l + 1].nchunks) + 1u) >> 1;
+            if (upos >= static_cast<uint32_t>(p.a_units)) { upos -= p.a_units; ++uwrap; }
           }
-          uint32_t wrap = ub / p.a_units, pu = ub - wrap * p.a_units;
           fence_after_sync();
           tr.rec(0x1000u | (l << 8) | (b << 4));
           uint32_t acc = 0, u = 0;

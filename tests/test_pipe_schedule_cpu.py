@@ -19,7 +19,8 @@ SHIM = r"""
 extern "C" int stage_order(int n_jobs, int n_layers, int n_mt, int* out, int cap) {
   bbmpc::StageSeq s; s.init(n_jobs, n_layers, n_mt);
   int j, l, b, n = 0;
-  while (s.next(j, l, b)) { if (n < cap) { out[3 * n] = j; out[3 * n + 1] = l; out[3 * n + 2] = b; } ++n; }
+  int i = 0;
+  while (s.next(j, l, b, i)) { if (i != j % n_mt) return -1; if (n < cap) { out[3 * n] = j; out[3 * n + 1] = l; out[3 * n + 2] = b; } ++n; }
   return n;
 }
 """
