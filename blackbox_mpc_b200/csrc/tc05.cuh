@@ -229,6 +229,9 @@ __device__ __forceinline__ void mma_unit_ss_probe(uint32_t d_tmem, uint64_t a0, 
         "r"(two), "r"(commit0), "r"(commit1), "r"(probe0), "r"(parity0), "r"(probe1), "r"(parity1)
       : "memory");
 }
+#ifndef TC05_UNIT_BRANCH
+#define TC05_UNIT_BRANCH 0   // 1: branch around the unit instead of predicating every tcgen05 instruction (A/B)
+#endif
 // The common case of mma_unit_ss_probe — three passes, both K-chunks present — with every tcgen05 instruction guarded by
 // the elect predicate alone (no per-instruction runtime predicates: each one costs a VOTEU + predicate logic in SASS) and
 // the descriptors built from their 32-bit low words (the high word, SBO / version / swizzle, is one constant).
@@ -258,6 +261,18 @@ __device__ __forceinline__ void mma_unit_ss_probe_full(uint32_t d_tmem, uint32_t
       "add.u32 t, t, %6;\n\t mov.b64 a1l, {t, %5};\n\t"
       "add.u32 t, %4, %9;\n\t mov.b64 b1, {t, %5};\n\t"
       "add.u32 t, t, %7;\n\t mov.b64 b1l, {t, %5};\n\t"
+#if TC05_UNIT_BRANCH
+      "@!pe bra UNIT_DONE;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%2], a0, b0, %10, pacc;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%2], al, b0, %10, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%2], a0, bl, %10, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1, %10, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%2], a1l, b1, %10, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1l, %10, pt;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t"
+      "@pc1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%13];\n\t"
+      "UNIT_DONE:\n\t"
+#else
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], a0, b0, %10, pacc;\n\t"
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], al, b0, %10, pt;\n\t"
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], a0, bl, %10, pt;\n\t"
@@ -266,6 +281,7 @@ __device__ __forceinline__ void mma_unit_ss_probe_full(uint32_t d_tmem, uint32_t
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1l, %10, pt;\n\t"
       "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t"
       "@pc1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%13];\n\t"
+#endif
       "selp.u32 %0, 1, 0, q0;\n\t"
       "selp.u32 %1, 1, 0, q1;\n\t"
       "}"
