@@ -153,9 +153,8 @@ __device__ __forceinline__ void pconv_full(const uint32_t (&r)[16], uint32_t (&h
 template <int ACT, bool TR>
 __device__ __forceinline__ void pipe_convert(uint32_t taddr, int Npad, int N, int n_a_chunks, int sub, int passes,
                                             uint32_t aring, uint32_t chunk_bytes, uint32_t a_units, uint32_t pu, uint32_t wrap,
-                                            uint32_t bar_afull, uint32_t bar_afree, uint32_t bar_drained, uint32_t bar_adone, int row, int lane,
+                                            uint32_t bar_afull, uint32_t bar_afree, uint32_t bar_drained, int row, int lane,
                                             const float* tail_tab, int stagger, uint32_t polls, volatile uint32_t* dbgp, PTracer<TR>& tr) {
-  // bar_adone != 0 (two jobs in flight): the MMA issuer waits once for the whole operand instead of per ring unit
   const int n_full = N >> 4;        // chunks whose 16 columns are all real features
   const int n_data = Npad >> 4;     // chunks that carry accumulator data at all
   if (sub && stagger > 0) {
@@ -235,10 +234,6 @@ __device__ __forceinline__ void pipe_convert(uint32_t taddr, int Npad, int N, in
     tr.rec(0x300u | c);
   }
   if (sub >= n_data) drained();   // no chunk of this warp carried accumulator data
-  if (bar_adone) {                // every lane's stores are fenced (above) before its warp's arrival
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_adone);
-  }
 }
 
 template <int DS_T, int DU_T, bool TR, int ACT_T>
@@ -368,7 +363,6 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
       uint32_t upos = 0, uwrap = 0;         // ring position / wrap count of the next unit to allocate (mirrors the conversion warps)
       uint32_t dw0 = 0, dw1 = 0;            // stages issued into D[0] / D[1]
       uint32_t xc0 = 0, xc1 = 0, xc2 = 0;   // layer-0 inputs consumed per X region (barrier phases persist across rounds)
-      uint32_t ad0 = 0, ad1 = 0;            // whole-operand completions consumed per slot (two jobs in flight)
       const uint32_t wring16 = (smem_base + lay.wring) >> 4, stage16 = static_cast<uint32_t>(p.stage_bytes) >> 4;
       const uint32_t aring16 = (smem_base + lay.aring) >> 4, achunk16 = static_cast<uint32_t>(p.a_chunk_bytes) >> 4;
       constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);          // SBO = 128 B, descriptor version 1, no swizzle
@@ -408,19 +402,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
           uint32_t acc = 0, u = 0;
           const uint32_t n_units = (job.nchunks + 1u) >> 1;
           const uint32_t xcol = tmem_base + p.col_x + i * p.x_w;
-          // BBMPC_TC_X & 32: wait for the whole converted operand (bar_adone) instead of per ring unit.  Measured slower
-          // (1.356 vs 1.237 ms per C4 rollout): the stage then starts ~2k cycles later, after the last conversion step.
-          const bool whole = (p.xflags & 32) && !seq.single && l > 0;
-          if (whole) {
-            mbar_wait(bar_adone + 8 * b, (b ? ad1 : ad0) & 1u, dbgp, 0x1200000u | (j << 8) | l);
-            if (b) ++ad1; else ++ad0;
-            fence_after_sync();
-          }
+          // (Waiting once for the whole converted operand instead of per ring unit measured slower — 1.356 vs 1.237 ms per
+          // C4 rollout: the stage then starts ~2k cycles later, after the last conversion step — and was removed.)
           // Readiness of the CURRENT unit's weight stage / ring unit, learnt from the probe issued with the previous unit
           // (ok_w only matters at the first unit of a group, ok_a at every unit of a layer >= 1 in single mode).
           uint32_t ok_w = 0, ok_a = 0;
 #if PIPE_ISSUE_VARIANT == 0
-          if (l > 0 && three && !whole) {
+          if (l > 0 && three) {
             // Layers >= 1: flat loop over the ring units, addresses advance by constants (the issuing warp shares its
             // scheduler with two conversion warps: every instruction of this loop is paid ~10 cycles).  A weight group
             // (ring stage) holds n >= 1 units: wide layers one, the output layer several.
@@ -489,7 +477,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
                 __syncwarp();
                 ok_w = 0;
               } else {
-                if (!whole && !ok_a) mbar_wait_poll(bar_afull + 8 * pu, wrap & 1u, dbgp, 0x2000000u | (j << 12) | (l << 8) | u);
+                if (!ok_a) mbar_wait_poll(bar_afull + 8 * pu, wrap & 1u, dbgp, 0x2000000u | (j << 12) | (l << 8) | u);
                 fence_after_sync();
                 tr.rec(0x4200u | u);
                 uint32_t pn = pu + 1, wn = wrap;
@@ -509,13 +497,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
                                     bar_afree + 8 * pu, last_of_group ? bar_wempty + 8 * stage : 0u,
                                     bar_wfull + 8 * nstage, nphase, bar_afull + 8 * pn, wn & 1u, pw, pa);
                 ok_w = (last_of_group && g + 1 < job.ngroups) ? pw : 0u;
-                ok_a = (!whole && u + 1 < n_units) ? pa : 0u;
+                ok_a = (u + 1 < n_units) ? pa : 0u;
 #else
                 // A/B: C++ elected block (PIPE_ISSUE_VARIANT 1: probes issued before it, 2: no probes)
                 uint32_t pw = 0, pa = 0;
                 if (PIPE_ISSUE_VARIANT == 1) {
                   pw = (last_of_group && g + 1 < job.ngroups) ? mbar_test_wait(bar_wfull + 8 * nstage, nphase) : 0u;
-                  pa = (!whole && u + 1 < n_units) ? mbar_test_wait(bar_afull + 8 * pn, wn & 1u) : 0u;
+                  pa = (u + 1 < n_units) ? mbar_test_wait(bar_afull + 8 * pn, wn & 1u) : 0u;
                 }
                 if (elect_one()) {
                   mma_ss(d, a0, b0, job.idesc, acc);
@@ -845,7 +833,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
         tr.rec(0x20u | (l << 8) | (b << 12));
         const uint32_t aring = smem_base + lay.aring;
 #define PIPE_CONV(ACT) pipe_convert<ACT, TR>(taddr, Npad, N, n_a_chunks, sub, p.passes, aring, p.a_chunk_bytes, p.a_units, pu, wrap, \
-                                            bar_afull, bar_afree, bar_drained + 8 * b, (seq.single || !(p.xflags & 32)) ? 0u : bar_adone + 8 * b, row_in_tile, lane, tail_tab, p.stagger, p.dfull_polls, dbgp, tr)
+                                            bar_afull, bar_afree, bar_drained + 8 * b, row_in_tile, lane, tail_tab, p.stagger, p.dfull_polls, dbgp, tr)
         if (ACT_T >= 0) {
           PIPE_CONV((ACT_T >= 0 ? ACT_T : 0));
         } else {

@@ -8,6 +8,9 @@
 namespace bbmpc {
 using namespace tc05;
 
+#ifndef BBMPC_POLL_SPINS
+#define BBMPC_POLL_SPINS (1u << 25)
+#endif
 #ifndef BBMPC_RCP_MUFU
 #define BBMPC_RCP_MUFU 1   // 0: reciprocal on the FMA pipe (measured slower, see BBMPC_LO_CVT)
 #endif
@@ -32,7 +35,7 @@ __device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity
 __device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity, volatile uint32_t* dbg = nullptr, uint32_t tag = 0) {
   uint32_t spins = 0;
   while (!mbar_test_wait(bar, parity)) {
-    if (++spins > (1u << 25)) {
+    if (++spins > BBMPC_POLL_SPINS) {
       if (dbg) {
         const uint32_t slot = 8u * (threadIdx.x >> 5) + 256u * (blockIdx.x & 1);
         dbg[slot + 0] = 0xDEAD0000u | threadIdx.x; dbg[slot + 1] = bar; dbg[slot + 2] = parity; dbg[slot + 3] = tag;
