@@ -45,9 +45,6 @@
 namespace bbmpc {
 using namespace tc05;
 
-#ifndef PIPE_ISSUE_VARIANT
-#define PIPE_ISSUE_VARIANT 0   // how the MMA issuer emits a ring unit (A/B builds, tools/debug/build_variant.sh)
-#endif
 constexpr int PIPE_WARPS = 20;
 constexpr int PIPE_THREADS = 32 * PIPE_WARPS;
 constexpr int PIPE_MAX_MT = 3;          // member-tiles per CTA and round
@@ -407,7 +404,6 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
           // Readiness of the CURRENT unit's weight stage / ring unit, learnt from the probe issued with the previous unit
           // (ok_w only matters at the first unit of a group, ok_a at every unit of a layer >= 1 in single mode).
           uint32_t ok_w = 0, ok_a = 0;
-#if PIPE_ISSUE_VARIANT == 0
           if (l > 0 && three) {
             // Layers >= 1: flat loop over the ring units, addresses advance by constants (the issuing warp shares its
             // scheduler with two conversion warps: every instruction of this loop is paid ~10 cycles).  A weight group
@@ -447,7 +443,6 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
               }
             }
           } else
-#endif
           for (uint32_t g = 0; g < job.ngroups; ++g) {
             const uint32_t n = (job.gsz >> (4 * g)) & 15u;
             tr.rec(0x4000u | g);
@@ -484,41 +479,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
                 if (pn == static_cast<uint32_t>(p.a_units)) { pn = 0; ++wn; }
                 const uint32_t alo = a_desc_lo_base | ((aring16 + 2 * pu * achunk16) & 0x3FFFu);
                 const uint64_t a0 = (static_cast<uint64_t>(DESC_HI) << 32) | alo;
-#if PIPE_ISSUE_VARIANT == 0
-                // one asm block: probes of the next group's weight stage and (single mode) the next ring unit first, the
-                // unit's MMAs and commits by one elected lane, the probe results last (their latency overlaps the issue)
+                // (single-pass precision only: layers >= 1 with three passes take the flat loop above)
                 uint32_t pw = 0, pa = 0;
-                if (three && two)   // the common case: a slimmer instruction stream (the issuing warp paces the whole CTA)
-                  mma_unit_ss_probe_full(d, alo, blo, DESC_HI, a_lo_off16, job.lo_off16, achunk16, job.chunk16, job.idesc, acc,
-                                         bar_afree + 8 * pu, last_of_group ? bar_wempty + 8 * stage : 0u,
-                                         bar_wfull + 8 * nstage, nphase, bar_afull + 8 * pn, wn & 1u, pw, pa);
-                else
-                  mma_unit_ss_probe(d, a0, b0, a_lo_off16, job.lo_off16, achunk16, job.chunk16, job.idesc, acc, three ? 1u : 0u, two ? 1u : 0u,
-                                    bar_afree + 8 * pu, last_of_group ? bar_wempty + 8 * stage : 0u,
-                                    bar_wfull + 8 * nstage, nphase, bar_afull + 8 * pn, wn & 1u, pw, pa);
+                mma_unit_ss_probe(d, a0, b0, a_lo_off16, job.lo_off16, achunk16, job.chunk16, job.idesc, acc, three ? 1u : 0u, two ? 1u : 0u,
+                                  bar_afree + 8 * pu, last_of_group ? bar_wempty + 8 * stage : 0u,
+                                  bar_wfull + 8 * nstage, nphase, bar_afull + 8 * pn, wn & 1u, pw, pa);
                 ok_w = (last_of_group && g + 1 < job.ngroups) ? pw : 0u;
                 ok_a = (u + 1 < n_units) ? pa : 0u;
-#else
-                // A/B: C++ elected block (PIPE_ISSUE_VARIANT 1: probes issued before it, 2: no probes)
-                uint32_t pw = 0, pa = 0;
-                if (PIPE_ISSUE_VARIANT == 1) {
-                  pw = (last_of_group && g + 1 < job.ngroups) ? mbar_test_wait(bar_wfull + 8 * nstage, nphase) : 0u;
-                  pa = (u + 1 < n_units) ? mbar_test_wait(bar_afull + 8 * pn, wn & 1u) : 0u;
-                }
-                if (elect_one()) {
-                  mma_ss(d, a0, b0, job.idesc, acc);
-                  if (three) { mma_ss(d, a0 + a_lo_off16, b0, job.idesc, 1u); mma_ss(d, a0, b0 + job.lo_off16, job.idesc, 1u); }
-                  if (two) {
-                    const uint64_t a1 = a0 + achunk16, b1 = b0 + job.chunk16;
-                    mma_ss(d, a1, b1, job.idesc, 1u);
-                    if (three) { mma_ss(d, a1 + a_lo_off16, b1, job.idesc, 1u); mma_ss(d, a1, b1 + job.lo_off16, job.idesc, 1u); }
-                  }
-                  mma_commit(bar_afree + 8 * pu);
-                  if (last_of_group) mma_commit(bar_wempty + 8 * stage);
-                }
-                __syncwarp();
-                ok_w = pw; ok_a = pa;
-#endif
                 pu = pn; wrap = wn;
               }
               acc = 1u;
