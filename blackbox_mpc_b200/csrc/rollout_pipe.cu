@@ -427,9 +427,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) rollout_pipe_kernel(const __g
                                        bar_afree + 8 * pu, last ? bar_wempty + 8 * stage : 0u, bar_wfull + 8 * nstage, nphase,
                                        bar_afull + 8 * pn, wn & 1u, pw, pa);
               else
-                mma_unit_ss_probe(d, (static_cast<uint64_t>(DESC_HI) << 32) | alo, (static_cast<uint64_t>(DESC_HI) << 32) | blo, a_lo_off16,
-                                  job.lo_off16, achunk16, job.chunk16, job.idesc, acc, 1u, 0u, bar_afree + 8 * pu,
-                                  last ? bar_wempty + 8 * stage : 0u, bar_wfull + 8 * nstage, nphase, bar_afull + 8 * pn, wn & 1u, pw, pa);
+                mma_unit_ss_probe_half(d, alo, blo, DESC_HI, a_lo_off16, job.lo_off16, job.idesc, acc, bar_afree + 8 * pu,
+                                       last ? bar_wempty + 8 * stage : 0u, bar_wfull + 8 * nstage, nphase, bar_afull + 8 * pn, wn & 1u, pw, pa);
               ok_a = more ? pa : 0u;
               alo = pn ? alo + astep : alo0;
               pu = pn; wrap = wn; acc = 1u;

@@ -290,6 +290,42 @@ __device__ __forceinline__ void mma_unit_ss_probe_full(uint32_t d_tmem, uint32_t
         "r"(commit0), "r"(commit1), "r"(probe0), "r"(parity0), "r"(probe1), "r"(parity1)
       : "memory");
 }
+// Same for a unit that holds ONE K-chunk (the last unit of a layer with an odd number of chunks): three MMAs.
+__device__ __forceinline__ void mma_unit_ss_probe_half(uint32_t d_tmem, uint32_t a0_lo, uint32_t b0_lo, uint32_t desc_hi, uint32_t a_lo,
+                                                       uint32_t b_lo, uint32_t idesc, uint32_t acc, uint32_t commit0, uint32_t commit1,
+                                                       uint32_t probe0, uint32_t parity0, uint32_t probe1, uint32_t parity1,
+                                                       uint32_t& ok0, uint32_t& ok1) {
+  // %0 ok0, %1 ok1 | %2 d, %3 a0_lo, %4 b0_lo, %5 desc_hi, %6 a_lo, %7 b_lo, %8 idesc, %9 acc, %10 commit0, %11 commit1,
+  // %12 probe0, %13 parity0, %14 probe1, %15 parity1
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q0, q1, pe, pacc, pc1, pt;\n\t"
+      ".reg .b32 t;\n\t"
+      ".reg .b64 a0, b0, al, bl;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q0, [%12], %13;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q1, [%14], %15;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pacc, %9, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "setp.ne.b32 pc1, %11, 0;\n\t"
+      "and.pred pc1, pc1, pe;\n\t"
+      "mov.b64 a0, {%3, %5};\n\t"
+      "mov.b64 b0, {%4, %5};\n\t"
+      "add.u32 t, %3, %6;\n\t mov.b64 al, {t, %5};\n\t"
+      "add.u32 t, %4, %7;\n\t mov.b64 bl, {t, %5};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], a0, b0, %8, pacc;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], al, b0, %8, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], a0, bl, %8, pt;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t"
+      "@pc1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t"
+      "selp.u32 %0, 1, 0, q0;\n\t"
+      "selp.u32 %1, 1, 0, q1;\n\t"
+      "}"
+      : "=r"(ok0), "=r"(ok1)
+      : "r"(d_tmem), "r"(a0_lo), "r"(b0_lo), "r"(desc_hi), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(commit0), "r"(commit1),
+        "r"(probe0), "r"(parity0), "r"(probe1), "r"(parity1)
+      : "memory");
+}
 // All previously issued MMAs of this thread arrive (count 1) on `bar` when they complete.
 // Implies tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
