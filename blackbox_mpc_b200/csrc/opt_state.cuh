@@ -10,6 +10,7 @@ struct bbmpc_opt {
   int p0 = 0, P_local = 0;        // this rank's slice [p0, p0 + P_local) of the population
   int n_eval = 0;                 // rows of the population axis handed to the evaluator (SPSA: 2*P_local)
   int HU = 0, AHU = 0;            // H*dU, A*H*dU
+  bool cem_fuse = false, cem_fused_done = false;   // bbmpc_opt_call: CEM top-E + refit as one kernel (iter_merge then has nothing to do)
   int cem_slices = 1;             // population slices of the last unsharded CEM top-E (their messages sit back to back in d_partial)
   uint32_t act_call = 0;          // host mirror of *d_act_ctr
   uint32_t* d_act_ctr = nullptr;  // act() calls completed so far (Philox counter word), bumped by the last kernel of every call

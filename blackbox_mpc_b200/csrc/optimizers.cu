@@ -220,6 +220,47 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_partial_kernel(const float* 
   }
 }
 
+// ---- CEM top-E + refit in ONE kernel for the unsharded act() (no message, no second launch): the elite rows are staged
+// in shared memory by the whole CTA, then mean / ddof-0 variance / alpha blend with exactly the arithmetic (and the
+// summation order: elite order = reward descending, row ascending) of cem_refit_kernel, so that sharded and
+// unsharded runs stay bit-identical.  elite_cache: E*HU floats of dynamic shared memory behind the key cache, or 0.
+__global__ void __launch_bounds__(SEL_THREADS) cem_topk_refit_kernel(const float* returns, const float* samples, int P_local, int A, int HU,
+                                                                     int E, int use_cache, int key_words, int elite_cache, float alpha,
+                                                                     float* mean, float* var) {
+  __shared__ int hist[256];
+  __shared__ int misc[40];
+  __shared__ uint32_t keys[SEL_MAX_K];
+  __shared__ int idx[SEL_MAX_K];
+  extern __shared__ uint32_t topk_kcache[];
+  const int a = blockIdx.x;
+  const SelectScratch sc{hist, misc, keys, idx};
+  block_topk(returns + a, P_local, A, E, sc, use_cache ? topk_kcache : nullptr);
+  __syncthreads();
+  float* elite = reinterpret_cast<float*>(topk_kcache + key_words);
+  if (elite_cache)
+    for (int i = threadIdx.x; i < E * HU; i += SEL_THREADS) {
+      const int k = i / HU, e = i - k * HU, p = idx[k];
+      elite[i] = (p != 0x7FFFFFFF) ? samples[(static_cast<size_t>(p) * A + a) * HU + e] : 0.0f;
+    }
+  __syncthreads();
+  for (int e = threadIdx.x; e < HU; e += SEL_THREADS) {
+    auto at = [&](int k) -> float {
+      if (elite_cache) return elite[k * HU + e];
+      const int p = idx[k];
+      return (p != 0x7FFFFFFF) ? samples[(static_cast<size_t>(p) * A + a) * HU + e] : 0.0f;
+    };
+    float sum = 0.0f;
+    for (int k = 0; k < E; ++k) sum += at(k);
+    const float nm = __fdiv_rn(sum, static_cast<float>(E));
+    float sq = 0.0f;
+    for (int k = 0; k < E; ++k) { const float d = __fsub_rn(at(k), nm); sq += __fmul_rn(d, d); }
+    const float nv = __fdiv_rn(sq, static_cast<float>(E));
+    const float one_m = __fsub_rn(1.0f, alpha);
+    mean[a * HU + e] = __fadd_rn(__fmul_rn(alpha, mean[a * HU + e]), __fmul_rn(one_m, nm));
+    var[a * HU + e] = __fadd_rn(__fmul_rn(alpha, var[a * HU + e]), __fmul_rn(one_m, nv));
+  }
+}
+
 // ---- CEM merge + refit (cem.py:98-125).  One CTA per agent; candidates = world x E records.
 __global__ void __launch_bounds__(SEL_THREADS) cem_refit_kernel(const float* partials, int world, int A, int HU,
                                                                 int E, float alpha, float* mean, float* var,
@@ -561,6 +602,16 @@ void launch_topk_partial(const float* returns, const float* samples, float* part
   topk_partial_kernel<<<dim3(A, n_slices), SEL_THREADS, use_cache ? per * sizeof(uint32_t) : 0, st>>>(returns, samples, partial, P_local, p0, A, HU, E,
                                                                                                     use_cache, slice_stride);
 }
+void launch_cem_topk_refit(const float* returns, const float* samples, int P_local, int A, int HU, int E, float alpha, float* mean,
+                           float* var, cudaStream_t st) {
+  cudaFuncSetAttribute(cem_topk_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  const int use_cache = (P_local > 0 && P_local + 1 <= 16384) ? 1 : 0;
+  const int key_words = use_cache ? P_local + 1 : 0;
+  const size_t elite_bytes = static_cast<size_t>(E) * HU * sizeof(float);
+  const int elite_cache = (key_words * sizeof(uint32_t) + elite_bytes <= 160 * 1024) ? 1 : 0;
+  cem_topk_refit_kernel<<<A, SEL_THREADS, key_words * sizeof(uint32_t) + (elite_cache ? elite_bytes : 0), st>>>(
+      returns, samples, P_local, A, HU, E, use_cache, key_words, elite_cache, alpha, mean, var);
+}
 }  // namespace bbmpc
 
 // ============================================================================ host orchestration
@@ -825,6 +876,11 @@ int bbmpc_opt_iter_local(bbmpc_opt* o, int iter, float* partial_out, void* strea
       // unsharded, internal message buffer: the local rows are cut into slices, one CTA each (a single CTA scanning
       // 10 000 returns took 34 us per iteration); bbmpc_opt_iter_merge ranks the slices' candidates like ranks'
       o->cem_slices = (!partial_out && o->world == 1) ? cem_slice_count(o) : 1;
+      if (o->cem_fuse && !partial_out && o->world == 1 && o->cem_slices == 1) {   // inside bbmpc_opt_call: top-E and refit in one kernel
+        launch_cem_topk_refit(o->d_returns, o->d_samples, o->P_local, A, HU, c.num_elite, c.alpha, o->d_mean, o->d_var, st);
+        o->cem_fused_done = true;
+        break;
+      }
       launch_topk_partial(o->d_returns, o->d_samples, partial, o->P_local, o->p0, A, HU, c.num_elite, st, o->cem_slices, partial_floats(o));
       break;
     case BBMPC_OPT_PI2:
@@ -868,6 +924,7 @@ int bbmpc_opt_iter_merge(bbmpc_opt* o, int iter, const float* partials, int worl
   switch (c.kind) {
     case BBMPC_OPT_CEM:
       if (world * c.num_elite > SEL_MAX_K) return opt_fail(o, BBMPC_EINVAL, "world*num_elite exceeds 1024");
+      if (o->cem_fused_done) { o->cem_fused_done = false; return BBMPC_OK; }   // refit already done by cem_topk_refit_kernel
       cem_refit_kernel<<<A, SEL_THREADS, 0, st>>>(in, (!partials && world == 1) ? o->cem_slices : world, A, HU, c.num_elite, c.alpha, o->d_mean, o->d_var, stride);
       break;
     case BBMPC_OPT_PI2:
@@ -962,8 +1019,11 @@ static int opt_call_body(bbmpc_opt* o, int time_step, int add_noise, void* strea
       if (int rc = bbmpc_opt_iter_merge(o, it, o->d_gather, o->world, stream)) return rc;
       continue;
     }
-    if (int rc = bbmpc_opt_iter_local(o, it, nullptr, stream)) return rc;
-    if (int rc = bbmpc_opt_iter_merge(o, it, nullptr, 1, stream)) return rc;
+    o->cem_fuse = !getenv("BBMPC_NO_CEM_FUSE");
+    int rc = bbmpc_opt_iter_local(o, it, nullptr, stream);
+    o->cem_fuse = false;
+    if (rc) return rc;
+    if ((rc = bbmpc_opt_iter_merge(o, it, nullptr, 1, stream))) return rc;
   }
   return bbmpc_opt_finish(o, add_noise, o->d_action, o->d_next, o->d_reward, stream);
 }

@@ -283,3 +283,30 @@ def test_graph_replay_equals_eager(cuda_device, monkeypatch, opt_name):
             assert torch.equal(x, y), f"act() call {t} differs between the eager and the replayed path"
     # consecutive calls differ (fresh draws), except for optimizers whose answer does not depend on the draws' index
     assert not torch.equal(graphed[3][0], graphed[4][0]) or opt_name == "SPSA"
+
+
+@pytest.mark.parametrize("name,P,A", [("C2", 300, 2), ("C4", 1000, 1)])
+def test_cem_fused_topk_refit_equals_split_kernels(cuda_device, monkeypatch, name, P, A):
+    """Inside bbmpc_opt_call an unsharded CEM iteration selects the elites and refits mean / variance in ONE kernel
+    (cem.py:98-125); the split kernels (local top-E message + merge / refit, the form every sharded run uses) must give the
+    same bits: identical elite order, identical summation order."""
+    w = workloads.make(name, population_size=P, num_agents=A, bias_scale=0.1)
+    state = torch.from_numpy(w.state)
+
+    def run():
+        policy = workloads.build_policy(w, precision="fp32")
+        opt = policy._optimizer
+        outs = []
+        for t in range(3):
+            a, n, r = opt(state, t, False)
+            outs.append((a.cpu().clone(), opt.get_tensor("mean").cpu().clone(), opt.get_tensor("variance").cpu().clone()))
+        return outs, opt._engine.launch_count
+
+    monkeypatch.setenv("BBMPC_NO_CEM_FUSE", "1")
+    split, launches_split = run()
+    monkeypatch.delenv("BBMPC_NO_CEM_FUSE")
+    fused, launches_fused = run()
+    assert launches_fused < launches_split
+    for t, (s, f) in enumerate(zip(split, fused)):
+        for x, y in zip(s, f):
+            assert torch.equal(x, y), f"act() call {t}: fused and split CEM refit differ"
