@@ -105,10 +105,31 @@ __device__ inline void block_topk(const float* __restrict__ vals, int n, int str
       if ((ky & mask) == prefix) atomicAdd(&sc.hist[(ky >> shift) & 255], 1);
     }
     __syncthreads();
-    if (tid == 0) {
-      int cum = 0, b = 255;
-      for (; b > 0; --b) { if (cum + sc.hist[b] >= need) break; cum += sc.hist[b]; }
-      sc.misc[34] = b; sc.misc[35] = need - cum;
+    if (tid < 32) {
+      // bucket b with  sum(hist[b+1..255]) < need <= sum(hist[b..255])  (b = 0 if the sum never reaches need), by one warp:
+      // lane L owns buckets 255-8L .. 248-8L (descending), suffix sums across the lanes with shuffles
+      int h[8], mine = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { h[q] = sc.hist[255 - 8 * tid - q]; mine += h[q]; }
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += v;
+      }
+      int cum = incl - mine;                          // buckets above this lane's
+      const bool here = cum < need && incl >= need;   // the crossing lies in this lane's eight buckets
+      const unsigned ball = __ballot_sync(0xffffffffu, here);
+      if (ball == 0u) { if (tid == 31) { sc.misc[34] = 0; sc.misc[35] = need - (incl - h[7]); } }   // never reached: bucket 0 takes the rest
+      else if (here) {
+        int b = 255 - 8 * tid;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (cum + h[q] >= need) break;
+          cum += h[q]; --b;
+        }
+        sc.misc[34] = b; sc.misc[35] = need - cum;
+      }
     }
     __syncthreads();
     prefix |= static_cast<uint32_t>(sc.misc[34]) << shift;
@@ -124,9 +145,24 @@ __device__ inline void block_topk(const float* __restrict__ vals, int n, int str
     const uint32_t ky = key_at(i);
     if (ky > T) { const int slot = atomicAdd(&sc.misc[36], 1); sc.out_keys[slot] = ky; sc.out_idx[slot] = i; }
   }
-  // ties at the threshold: ordered scan so the lowest indices win
+  // ties at the threshold.  Usually every key equal to T is taken (a unique threshold value: need == 1 == number of ties):
+  // then the slot order does not matter (the final sort is by (key, index)) and one atomic counter places them.
+  if (tid == 0) sc.misc[37] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += SEL_THREADS)
+    if (key_at(i) == T) atomicAdd(&sc.misc[37], 1);
+  __syncthreads();
+  const int n_ties = sc.misc[37];
+  __syncthreads();
+  if (n_ties <= need) {
+    if (tid == 0) sc.misc[37] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += SEL_THREADS)
+      if (key_at(i) == T) { const int slot = n_greater + atomicAdd(&sc.misc[37], 1); sc.out_keys[slot] = T; sc.out_idx[slot] = i; }
+  }
+  // more ties than places: ordered scan so the lowest indices win
   int taken = 0;
-  for (int base = 0; base < n && taken < need; base += SEL_THREADS) {
+  for (int base = 0; n_ties > need && base < n && taken < need; base += SEL_THREADS) {
     const int i = base + tid;
     const int flag = (i < n && key_at(i) == T) ? 1 : 0;
     int total;

@@ -310,3 +310,34 @@ def test_cem_fused_topk_refit_equals_split_kernels(cuda_device, monkeypatch, nam
     for t, (s, f) in enumerate(zip(split, fused)):
         for x, y in zip(s, f):
             assert torch.equal(x, y), f"act() call {t}: fused and split CEM refit differ"
+
+
+def test_cem_elites_follow_top_k_tie_rule(cuda_device, monkeypatch):
+    """tf.nn.top_k takes the LOWEST indices among equal values (cem.py:98-101).  A reward quantised to integers makes most
+    returns tie, also at the elite threshold (more ties than places left): the elite rows written by the selection kernel
+    must be the first E of a stable sort by (return descending, population row ascending)."""
+    from blackbox_mpc_b200.utils import rewards
+    monkeypatch.setenv("BBMPC_NO_CEM_FUSE", "1")       # the split kernels leave the elite records in the message buffer
+    monkeypatch.setenv("BBMPC_NO_GRAPH", "1")
+    src = "__device__ float reward(const float* s, const float* a, const float* s2) { return floorf(3.0f * a[0]); }"
+    P, E = 3000, 50
+    w = workloads.make("C2", population_size=P, planning_horizon=4, bias_scale=0.1)
+    w.max_iterations = 1
+    w.optimizer_args = dict(num_elite=E, alpha=0.25)
+    from blackbox_mpc_b200.policies.mpc_policy import MPCPolicy
+    base = workloads.build_policy(w, precision="fp32")
+    policy = MPCPolicy(reward_function=rewards.cuda_reward(src), env_action_space=base._optimizer._env_action_space,
+                       env_observation_space=base._optimizer._env_observation_space,
+                       dynamics_handler=base._trajectory_evaluator._system_dynamics_handler, optimizer_name="CEM",
+                       num_agents=1, planning_horizon=4, population_size=P, max_iterations=1, num_elite=E, alpha=0.25)
+    opt = policy._optimizer
+    opt(torch.from_numpy(w.state), 0, False)
+    returns = opt.get_tensor("returns").cpu().numpy().ravel()
+    rec = opt.get_tensor("partial").cpu().numpy().reshape(E, -1)
+    got_rows = rec[:, 1].view(np.int32)
+    order = np.lexsort((np.arange(P), -returns))[:E]
+    values, counts = np.unique(returns, return_counts=True)
+    assert counts.max() > E                       # heavy ties ...
+    assert (returns == returns[order[-1]]).sum() > (returns[order] == returns[order[-1]]).sum()   # ... also across the elite threshold
+    np.testing.assert_array_equal(got_rows, order.astype(np.int32))
+    np.testing.assert_array_equal(rec[:, 0], returns[order])
