@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(TR* NG) step_simt_kernel(const SimtParams p) {
 // over the warps and its features over the lanes (fp32 FMA, partial sums added in warp order).  The
 // last CTA to finish a row (arrival counter) sums the members in member order and applies
 // process_output + reward.
-constexpr int STEP_THREADS = 256;
+constexpr int STEP_THREADS = 1024;   // 32 warps: a 200-row layer is 7 weight rows per warp, all loads of a warp in flight at once
 constexpr int STEP_MAX_ROWS = 64;
 __global__ void __launch_bounds__(STEP_THREADS) step_mlp_kernel(const SimtParams p, float* __restrict__ scratch,
                                                                unsigned* __restrict__ counters) {
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_mlp_kernel(const SimtParams
     in[k] = v;
   }
   __syncthreads();
-  // K is split over the 8 warps (contiguous ranges), a lane owns output features lane, lane+32, ...: every
+  // K is split over the warps (contiguous ranges), a lane owns output features lane, lane+32, ...: every
   // weight is read exactly once, coalesced, and all loads of a warp are independent (the former one-thread-
   // per-feature loop was a chain of ~K/8 dependent DRAM round trips per layer: 286 us for the C4 ensemble).
   // The warps' partial sums are added in warp order, then bias and activation.
@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_mlp_kernel(const SimtParams
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+#pragma unroll 4
       for (int k = k0; k < k1; ++k) {
         const float x = in[k];
         const float* __restrict__ wr = W + static_cast<size_t>(k) * L.ldw + f0 + lane;
@@ -379,6 +380,7 @@ int launch_step_simt(bbmpc_ctx* ctx, const StepIO& io_in, cudaStream_t st) {
       BB_CUDA(ctx, cudaMemset(ctx->step_counters, 0, sizeof(unsigned) * STEP_MAX_ROWS));
     }
     const size_t sb = sizeof(float) * (2 + STEP_THREADS / 32) * static_cast<size_t>(p.mlp.max_width > MAX_DS ? p.mlp.max_width : MAX_DS);
+    if (int rc = set_smem(ctx, step_mlp_kernel, sb)) return rc;
     step_mlp_kernel<<<dim3(io.B, p.mlp.n_members), STEP_THREADS, sb, st>>>(p, ctx->step_scratch, ctx->step_counters);
     BB_LAUNCH_CHECK(ctx);
     return BBMPC_OK;
