@@ -556,7 +556,7 @@ __global__ void p2p_publish_kernel(uint32_t* flag, uint32_t seq) {
 // `src_stride` (a multiple of 4 floats) separates the two parity copies of a message inside a rank's exchange buffer, so
 // the 16-byte loads are aligned for any message length; the gathered copies stay dense (n_floats apart), hence the
 // vector path only when n_floats itself is a multiple of 4.
-__global__ void __launch_bounds__(256) p2p_gather_kernel(float* const* peers, float* gathered, int n_floats, int src_stride,
+__global__ void __launch_bounds__(1024) p2p_gather_kernel(float* const* peers, float* gathered, int n_floats, int src_stride,
                                                          size_t flag_off_floats, uint32_t seq, int parity) {
   const int g = blockIdx.x;
   const float* src_base = peers[g];
@@ -573,10 +573,22 @@ __global__ void __launch_bounds__(256) p2p_gather_kernel(float* const* peers, fl
   const int n_vec = (n_floats & 3) == 0 ? n_floats / 4 : 0;
   const float4* src = reinterpret_cast<const float4*>(msg);
   float4* dst = reinterpret_cast<float4*>(gathered + static_cast<size_t>(g) * n_floats);
-  for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
-    float4 v;
-    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + i) : "memory");
-    dst[i] = v;
+  // four peer loads in flight per thread before the first store: a load over NVLink is a ~2 us round trip, and a
+  // load -> store -> load chain per thread made the gather of a 36 KB message take nine of them
+  constexpr int U = 4;
+  for (int i0 = threadIdx.x; i0 < n_vec; i0 += U * blockDim.x) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < n_vec)
+        asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(src + i) : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < n_vec) dst[i] = v[u];
+    }
   }
   for (int i = 4 * n_vec + threadIdx.x; i < n_floats; i += blockDim.x) {
     float v;
@@ -1015,7 +1027,7 @@ static int opt_call_body(bbmpc_opt* o, int time_step, int add_noise, void* strea
       if (int rc = bbmpc_opt_iter_local(o, it, o->p2p_buf + static_cast<size_t>(parity) * stride4, stream)) return rc;
       const size_t flag_off = 2 * static_cast<size_t>(stride4);
       p2p_publish_kernel<<<1, 1, 0, st>>>(reinterpret_cast<uint32_t*>(o->p2p_buf + flag_off), seq); BB_LAUNCH_CHECK(o->ctx);
-      p2p_gather_kernel<<<o->world, 256, 0, st>>>(o->d_peer, o->d_gather, nf, stride4, flag_off, seq, parity); BB_LAUNCH_CHECK(o->ctx);
+      p2p_gather_kernel<<<o->world, 1024, 0, st>>>(o->d_peer, o->d_gather, nf, stride4, flag_off, seq, parity); BB_LAUNCH_CHECK(o->ctx);
       if (int rc = bbmpc_opt_iter_merge(o, it, o->d_gather, o->world, stream)) return rc;
       continue;
     }
