@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(SEL_THREADS) cem_topk_refit_kernel(const float
 // ---- CEM merge + refit (cem.py:98-125).  One CTA per agent; candidates = world x E records.
 __global__ void __launch_bounds__(SEL_THREADS) cem_refit_kernel(const float* partials, int world, int A, int HU,
                                                                 int E, float alpha, float* mean, float* var,
-                                                                int64_t partial_stride) {
+                                                                int64_t partial_stride, int elite_cache) {
   __shared__ uint32_t keys[SEL_MAX_K];
   __shared__ int gp[SEL_MAX_K];
   __shared__ int src[SEL_MAX_K];
@@ -289,18 +289,29 @@ __global__ void __launch_bounds__(SEL_THREADS) cem_refit_kernel(const float* par
     for (int i = threadIdx.x; i < n; i += SEL_THREADS) src[i] = i;  // local list is already sorted
   }
   __syncthreads();
-  // elites = first E in order; mean, ddof-0 variance in elite order; alpha blend
-  for (int e = threadIdx.x; e < HU; e += SEL_THREADS) {
-    float sum = 0.0f;
-    for (int k = 0; k < E; ++k) {
-      const int i = src[k];
-      sum += partials[(i / E) * partial_stride + (static_cast<size_t>(a) * E + (i % E)) * rec + 2 + e];
+  // elites = first E in order; mean, ddof-0 variance in elite order; alpha blend.  The E elite sequences are staged in
+  // shared memory by the whole CTA first (elite_cache: E*HU floats of dynamic shared memory, else read in place): HU
+  // threads each walking E rows twice was a chain of 2E dependent loads.
+  extern __shared__ float refit_elite[];
+  if (elite_cache) {
+    for (int t = threadIdx.x; t < E * HU; t += SEL_THREADS) {
+      const int k = t / HU, e = t - k * HU, i = src[k];
+      refit_elite[t] = partials[(i / E) * partial_stride + (static_cast<size_t>(a) * E + (i % E)) * rec + 2 + e];
     }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < HU; e += SEL_THREADS) {
+    auto at = [&](int k) -> float {
+      if (elite_cache) return refit_elite[k * HU + e];
+      const int i = src[k];
+      return partials[(i / E) * partial_stride + (static_cast<size_t>(a) * E + (i % E)) * rec + 2 + e];
+    };
+    float sum = 0.0f;
+    for (int k = 0; k < E; ++k) sum += at(k);
     const float nm = __fdiv_rn(sum, static_cast<float>(E));
     float sq = 0.0f;
     for (int k = 0; k < E; ++k) {
-      const int i = src[k];
-      const float d = __fsub_rn(partials[(i / E) * partial_stride + (static_cast<size_t>(a) * E + (i % E)) * rec + 2 + e], nm);
+      const float d = __fsub_rn(at(k), nm);
       sq += __fmul_rn(d, d);
     }
     const float nv = __fdiv_rn(sq, static_cast<float>(E));
@@ -937,7 +948,13 @@ int bbmpc_opt_iter_merge(bbmpc_opt* o, int iter, const float* partials, int worl
     case BBMPC_OPT_CEM:
       if (world * c.num_elite > SEL_MAX_K) return opt_fail(o, BBMPC_EINVAL, "world*num_elite exceeds 1024");
       if (o->cem_fused_done) { o->cem_fused_done = false; return BBMPC_OK; }   // refit already done by cem_topk_refit_kernel
-      cem_refit_kernel<<<A, SEL_THREADS, 0, st>>>(in, (!partials && world == 1) ? o->cem_slices : world, A, HU, c.num_elite, c.alpha, o->d_mean, o->d_var, stride);
+      {
+        const size_t eb = static_cast<size_t>(c.num_elite) * HU * sizeof(float);
+        const int elite_cache = eb <= 160 * 1024 ? 1 : 0;
+        if (elite_cache) cudaFuncSetAttribute(cem_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cem_refit_kernel<<<A, SEL_THREADS, elite_cache ? eb : 0, st>>>(in, (!partials && world == 1) ? o->cem_slices : world, A, HU, c.num_elite,
+                                                                     c.alpha, o->d_mean, o->d_var, stride, elite_cache);
+      }
       break;
     case BBMPC_OPT_PI2:
       pi2_merge_kernel<<<A, 256, 0, st>>>(in, world, A, HU, c.lamda, o->d_mean, stride);
