@@ -938,9 +938,9 @@ int launch_rollout_pipe(bbmpc_ctx* ctx, const float* states, const float* action
   const int nM = m.mlp.n_members;
   const long long ids = static_cast<long long>(p.n_tiles) * nM;
   // Launches that give every CTA at most one member-tile have nothing to interleave; there the one-tile-per-CTA kernel
-  // wins (its A operand stays in TMEM: an SS-mode MMA also fetches A from shared memory, (128 + N) / N times the operand
-  // bytes per instruction at the same 64 B/clk — measured 0.59 vs 0.46 ms for a 1 250-row C4 shard).  BBMPC_TC_PIPE=1 forces
-  // the pipelined kernel for every shape (tests, A/B).
+  // wins (its conversion writes the next operand in place in TMEM, chunk by chunk behind the MMAs, without the shared-memory
+  // ring and its handoffs — measured 0.59 vs 0.46 ms for a 1 250-row C4 shard; the SS-mode MMAs themselves run at the
+  // TS-mode rate, tools/probe/dual_issue_probe.cu).  BBMPC_TC_PIPE=1 forces the pipelined kernel for every shape (tests, A/B).
   {
     const char* force = getenv("BBMPC_TC_PIPE");
     if (ids <= ctx->sm_count && !(force && force[0] == '1')) return -100;
